@@ -1,0 +1,291 @@
+// extern "C" entry points — engine life cycle and the SSZ half of include/b200_consensus.h.
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "engine.h"
+#include "sha256.cuh"
+#include "ssz_plan.h"
+
+namespace b200 {
+
+Engine& engine() {
+    static Engine e;
+    return e;
+}
+
+namespace {
+
+// crypto::hash on the device: one thread, arbitrary length (parity helper; not a throughput path)
+__global__ void k_sha256_bytes(const uint8_t* data, size_t len, uint32_t* out_words) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t st[8], w[16];
+    sha256_init(st);
+    size_t nblocks = (len + 9 + 63) / 64;
+    for (size_t b = 0; b < nblocks; b++) {
+        for (int i = 0; i < 16; i++) {
+            uint32_t v = 0;
+            for (int k = 0; k < 4; k++) {
+                size_t pos = b * 64 + size_t(i) * 4 + size_t(k);
+                uint32_t byte = 0;
+                if (pos < len) byte = data[pos];
+                else if (pos == len) byte = 0x80;
+                else if (pos >= nblocks * 64 - 8) byte = uint32_t((uint64_t(len) * 8) >> (8 * (nblocks * 64 - 1 - pos))) & 0xff;
+                v = (v << 8) | byte;
+            }
+            w[i] = v;
+        }
+        sha256_compress(st, w);
+    }
+    for (int i = 0; i < 8; i++) out_words[i] = st[i];
+}
+
+struct Guard {
+    std::unique_lock<std::mutex> lk;
+    explicit Guard(Engine& e) : lk(e.mu) {}
+};
+
+int32_t check_ready(Engine& e) {
+    if (!e.ready) { e.last_error = "b200_init has not been called (or failed)"; return B200_ERR_NOT_INITIALIZED; }
+    cudaError_t ce = cudaSetDevice(e.device);
+    if (ce != cudaSuccess) { e.last_error = cudaGetErrorString(ce); return B200_ERR_CUDA; }
+    return B200_SUCCESS;
+}
+
+int32_t run_oneshot(Engine& e, SszPlan& plan, const std::vector<uint32_t>& outputs, uint8_t* out) {
+    return plan.run(e, e.arena, e.fields, e.planbuf, false, outputs, out);
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_state {
+    SszPlan plan;
+    std::vector<uint32_t> outputs;
+    DevBuf arena, fields, planbuf;
+    bool uploaded = false;
+};
+
+extern "C" {
+
+int32_t b200_init(int32_t device) {
+    Engine& e = engine();
+    Guard g(e);
+    if (e.ready) return e.device == device ? B200_SUCCESS : B200_ERR_BAD_ARG;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) {
+        e.last_error = std::string("no CUDA device: ") + cudaGetErrorString(ce);
+        return B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { e.last_error = "device index out of range"; return B200_ERR_BAD_ARG; }
+    B200_CUDA_TRY(cudaSetDevice(device));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaEventCreate(&e.ev0));
+    B200_CUDA_TRY(cudaEventCreate(&e.ev1));
+    e.device = device;
+    const char* a = getenv("B200_SSZ_MINB_VALIDATORS");
+    const char* b = getenv("B200_SSZ_MINB_STAGE");
+    set_ssz_tuning(a ? atoi(a) : 0, b ? atoi(b) : 0);
+    e.ready = true;
+    return ensure_zero_nodes(e);
+}
+
+void b200_shutdown(void) {
+    Engine& e = engine();
+    Guard g(e);
+    if (!e.ready) return;
+    cudaSetDevice(e.device);
+    cudaStreamSynchronize(e.stream);
+    e.arena.release(); e.fields.release(); e.planbuf.release(); e.staging.release();
+    if (e.d_zero) cudaFree(e.d_zero);
+    e.d_zero = nullptr;
+    cudaEventDestroy(e.ev0); cudaEventDestroy(e.ev1);
+    cudaStreamDestroy(e.stream); cudaStreamDestroy(e.copy_stream);
+    e.ready = false;
+}
+
+const char* b200_last_error(void) { return engine().last_error.c_str(); }
+uint64_t b200_launch_count(void) { return engine().launches; }
+float b200_last_kernel_ms(void) { return engine().last_kernel_ms; }
+
+int32_t b200_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!out || (!data && len)) return B200_ERR_BAD_ARG;
+    B200_CUDA_TRY(e.fields.reserve(len + 64));
+    B200_CUDA_TRY(e.staging.reserve(64));
+    if (len) B200_CUDA_TRY(cudaMemcpyAsync(e.fields.p, data, len, cudaMemcpyHostToDevice, e.stream));
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(e.fields.p) + ((len + 31) & ~size_t(31)));
+    k_sha256_bytes<<<1, 32, 0, e.stream>>>(static_cast<const uint8_t*>(e.fields.p), len, d_out);
+    e.launches++;
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(e.staging.p, d_out, 32, cudaMemcpyDeviceToHost, e.stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    const uint32_t* w = static_cast<const uint32_t*>(e.staging.p);
+    for (int k = 0; k < 8; k++) {
+        out[4 * k] = uint8_t(w[k] >> 24); out[4 * k + 1] = uint8_t(w[k] >> 16);
+        out[4 * k + 2] = uint8_t(w[k] >> 8); out[4 * k + 3] = uint8_t(w[k]);
+    }
+    return B200_SUCCESS;
+}
+
+int32_t b200_merkleize(const uint8_t* chunks, size_t n_chunks, uint64_t limit, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!out || (!chunks && n_chunks)) return B200_ERR_BAD_ARG;
+    if (limit == 0) limit = n_chunks ? n_chunks : 1;
+    if (n_chunks > limit) return B200_ERR_LIMIT;
+    SszPlan p;
+    std::vector<uint32_t> outs{p.wide_chunks(p.stage_field(chunks, 32 * n_chunks), n_chunks, depth_for(limit))};
+    return run_oneshot(e, p, outs, out);
+}
+
+int32_t b200_mix_in_length(const uint8_t root[32], uint64_t length, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!root || !out) return B200_ERR_BAD_ARG;
+    SszPlan p;
+    std::vector<uint32_t> outs{p.mix_in_length(p.leaf(root), length)};
+    return run_oneshot(e, p, outs, out);
+}
+
+int32_t b200_is_valid_merkle_branch(const uint8_t leaf[32], const uint8_t* branch, size_t depth, uint64_t index,
+                                    const uint8_t root[32], int32_t* ok) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!leaf || !root || !ok || (!branch && depth) || depth > 64) return B200_ERR_BAD_ARG;
+    SszPlan p;
+    uint32_t v = p.leaf(leaf);
+    for (size_t i = 0; i < depth; i++) {
+        uint32_t sib = p.leaf(branch + 32 * i);
+        v = ((index >> i) & 1) ? p.hash2(sib, v) : p.hash2(v, sib);
+    }
+    uint8_t got[32];
+    std::vector<uint32_t> outs{v};
+    rc = run_oneshot(e, p, outs, got);
+    if (rc) return rc;
+    *ok = memcmp(got, root, 32) == 0 ? 1 : 0;
+    return B200_SUCCESS;
+}
+
+int32_t b200_htr_validators(const uint8_t* ssz, size_t n, uint64_t limit, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!out || (!ssz && n)) return B200_ERR_BAD_ARG;
+    if (limit == 0) limit = n ? n : 1;
+    if (n > limit) return B200_ERR_LIMIT;
+    SszPlan p;
+    uint32_t r = p.wide_records(JOB_VALIDATORS, p.stage_field(ssz, 121 * n), n, depth_for(limit));
+    std::vector<uint32_t> outs{p.mix_in_length(r, n)};
+    return run_oneshot(e, p, outs, out);
+}
+
+int32_t b200_htr_packed(const uint8_t* data, size_t nbytes, uint64_t limit_chunks, int32_t is_list, uint64_t length,
+                        uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!out || (!data && nbytes)) return B200_ERR_BAD_ARG;
+    uint64_t n = (nbytes + 31) / 32;
+    if (limit_chunks == 0) limit_chunks = n ? n : 1;
+    if (n > limit_chunks) return B200_ERR_LIMIT;
+    SszPlan p;
+    uint32_t r = p.wide_chunks(p.stage_field(data, nbytes), n, depth_for(limit_chunks));
+    if (is_list) r = p.mix_in_length(r, length);
+    std::vector<uint32_t> outs{r};
+    return run_oneshot(e, p, outs, out);
+}
+
+int32_t b200_htr_beacon_state_deneb(const uint8_t* ssz, size_t len, int32_t preset, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!ssz || !out) return B200_ERR_BAD_ARG;
+    SszPlan p;
+    std::vector<uint32_t> outs;
+    rc = build_beacon_state_plan(p, ssz, len, preset, outs);
+    if (rc) { e.last_error = "malformed deneb BeaconState SSZ"; return rc; }
+    return run_oneshot(e, p, outs, out);
+}
+
+int32_t b200_state_upload_deneb(const uint8_t* ssz, size_t len, int32_t preset, b200_state** out_handle) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!ssz || !out_handle) return B200_ERR_BAD_ARG;
+    std::unique_ptr<b200_state> h(new b200_state());
+    rc = build_beacon_state_plan(h->plan, ssz, len, preset, h->outputs);
+    if (rc) { e.last_error = "malformed deneb BeaconState SSZ"; return rc; }
+    uint8_t root[32];
+    rc = h->plan.run(e, h->arena, h->fields, h->planbuf, false, h->outputs, root);  // uploads + first hash
+    if (rc) { h->arena.release(); h->fields.release(); h->planbuf.release(); return rc; }
+    h->uploaded = true;
+    *out_handle = h.release();
+    return B200_SUCCESS;
+}
+
+int32_t b200_state_root(b200_state* h, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!h || !h->uploaded || !out) return B200_ERR_BAD_ARG;
+    return h->plan.run(e, h->arena, h->fields, h->planbuf, true, h->outputs, out);
+}
+
+void b200_state_free(b200_state* h) {
+    if (!h) return;
+    Engine& e = engine();
+    Guard g(e);
+    if (e.ready) { cudaSetDevice(e.device); cudaStreamSynchronize(e.stream); }
+    h->arena.release(); h->fields.release(); h->planbuf.release();
+    delete h;
+}
+
+int32_t b200_htr_beacon_state_deneb_shard(const uint8_t* ssz, size_t len, int32_t preset, int32_t rank, int32_t world,
+                                          uint8_t* out_roots) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!ssz || !out_roots) return B200_ERR_BAD_ARG;
+    SszPlan p;
+    std::vector<uint32_t> outs;
+    rc = build_beacon_state_shard_plan(p, ssz, len, preset, rank, world, outs);
+    if (rc) return rc;
+    return run_oneshot(e, p, outs, out_roots);
+}
+
+int32_t b200_htr_beacon_state_deneb_combine(const uint8_t* ssz, size_t len, int32_t preset, int32_t world,
+                                            const uint8_t* all_roots, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!ssz || !all_roots || !out) return B200_ERR_BAD_ARG;
+    SszPlan p;
+    std::vector<uint32_t> outs;
+    rc = build_beacon_state_combine_plan(p, ssz, len, preset, world, all_roots, outs);
+    if (rc) return rc;
+    return run_oneshot(e, p, outs, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// SSZ Merkle stage kernels: job descriptors shared by the host planner (ssz_plan.cu) and the kernels.
+#pragma once
+#include <cstdint>
+
+namespace b200 {
+
+enum JobType : uint32_t {
+    JOB_REDUCE = 0,      // nodes/chunks -> nodes, nlev in {0,1,2,3} levels per thread, zero-hash padding
+    JOB_VALIDATORS = 1,  // 121-byte SSZ Validator records -> hash_tree_root(Validator)
+    JOB_PUBKEY48 = 2,    // 48-byte records -> hash_tree_root(ByteVector<48>) (1 hash)
+    JOB_PAIR64 = 3,      // 64-byte records (two-chunk containers, e.g. HistoricalSummary) -> 1 hash
+    JOB_ETH1DATA = 4,    // 72-byte Eth1Data records -> 3 hashes
+};
+
+struct Job {
+    const void* src;      // device pointer (16-byte aligned)
+    uint32_t* dst;        // device pointer into the node arena (word form, 8 words per node)
+    uint64_t n_in;        // input elements
+    uint32_t type;
+    uint32_t level;       // REDUCE: tree level of the inputs (selects the zero-hash used as padding)
+    uint32_t nlev;        // REDUCE: levels folded per thread (0 = convert only)
+    uint32_t raw;         // REDUCE: inputs are raw SSZ bytes (byte-swap on load) instead of word-form nodes
+    uint32_t block_begin; // first block of this job inside the stage launch
+    uint32_t pad_;
+};
+
+constexpr int kMaxJobsPerStage = 24;
+constexpr int kStageThreads = 256;
+
+struct StageDesc {
+    Job jobs[kMaxJobsPerStage];
+    int njobs;
+    uint32_t nblocks;
+    const uint32_t* zero_nodes;  // device: zero-subtree hashes, word form, 65 x 8 words
+};
+
+// finisher op: arena[dst] = H(arena[a] || arena[b]); indices are node indices into the arena
+struct FinOp {
+    uint32_t a, b, dst, pad_;
+};
+
+constexpr int kFinisherThreads = 1024;
+constexpr int kMaxWaves = 256;
+
+void set_ssz_tuning(int minb_validators, int minb_stage);
+void launch_validators(const Job& jb, void* stream);
+void launch_stage(const StageDesc& sd, void* stream);
+void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream);
+
+}  // namespace b200

@@ -1,0 +1,452 @@
+// Host planner + executor for device-side SSZ hash_tree_root (see ssz_plan.h).
+#include "ssz_plan.h"
+
+#include <algorithm>
+
+namespace b200 {
+
+static constexpr uint32_t kSmallBase = 65;
+static constexpr uint32_t kSmallCap = 8192;
+
+int depth_for(uint64_t n) {
+    int d = 0;
+    while ((uint64_t(1) << d) < n) d++;
+    return d;
+}
+
+static inline uint32_t be32(const uint8_t* p) {
+    return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3];
+}
+
+// ------------------------------------------------------------------------------------------------ building
+uint32_t SszPlan::leaf(const uint8_t chunk[32]) {
+    uint32_t i = uint32_t(small_words_.size() / 8);
+    for (int k = 0; k < 8; k++) small_words_.push_back(be32(chunk + 4 * k));
+    return kSmallBase + i;
+}
+uint32_t SszPlan::leaf_u64(uint64_t v) {
+    uint8_t c[32] = {0};
+    for (int i = 0; i < 8; i++) c[i] = uint8_t(v >> (8 * i));
+    return leaf(c);
+}
+uint32_t SszPlan::leaf_bytes(const uint8_t* p, size_t n) {
+    uint8_t c[32] = {0};
+    memcpy(c, p, n > 32 ? 32 : n);
+    return leaf(c);
+}
+int SszPlan::ready_wave(uint32_t idx) const {
+    auto it = ready_.find(idx);
+    return it == ready_.end() ? 0 : it->second;
+}
+uint32_t SszPlan::hash2(uint32_t a, uint32_t b) {
+    uint32_t dst = uint32_t(arena_alloc(1));
+    int w = std::max(ready_wave(a), ready_wave(b));
+    ops_.push_back(FinOp{a, b, dst, 0});
+    op_wave_.push_back(w);
+    ready_[dst] = w + 1;
+    return dst;
+}
+uint32_t SszPlan::merkle_small(std::vector<uint32_t> nodes, int level, int depth_target) {
+    if (nodes.empty()) return zero(depth_target);
+    while (level < depth_target) {
+        if (nodes.size() & 1) nodes.push_back(zero(level));
+        std::vector<uint32_t> up(nodes.size() / 2);
+        for (size_t i = 0; i < up.size(); i++) up[i] = hash2(nodes[2 * i], nodes[2 * i + 1]);
+        nodes.swap(up);
+        level++;
+    }
+    return nodes[0];
+}
+uint32_t SszPlan::container(const std::vector<uint32_t>& field_roots) {
+    return merkle_small(field_roots, 0, depth_for(field_roots.size()));
+}
+uint64_t SszPlan::stage_field(const uint8_t* src, size_t nbytes) {
+    uint64_t off = (field_next_ + 255) & ~uint64_t(255);
+    size_t padded = ((nbytes + 31) & ~size_t(31)) + 32;
+    field_next_ = off + padded;
+    if (nbytes) copies_.push_back(HostCopy{src, nbytes, off, padded - nbytes});
+    return off;
+}
+void SszPlan::add_job(size_t stage, const PJob& j) {
+    if (stages_.size() <= stage) stages_.resize(stage + 1);
+    stages_[stage].push_back(j);
+}
+
+uint32_t SszPlan::wide_nodes(PSrc src, bool raw, uint64_t n, int level, int depth_target, size_t s) {
+    if (n == 0) return zero(depth_target);
+    while (n > kHandoff && level < depth_target) {
+        uint32_t nlev = uint32_t(std::min(3, depth_target - level));
+        uint64_t n_out = (n + (uint64_t(1) << nlev) - 1) >> nlev;
+        PJob j;
+        j.type = JOB_REDUCE; j.src = src; j.dst = arena_alloc(n_out); j.n_in = n;
+        j.level = uint32_t(level); j.nlev = nlev; j.raw = raw ? 1 : 0;
+        add_job(s++, j);
+        src.in_arena = true; src.off = j.dst; raw = false;
+        n = n_out; level += int(nlev);
+    }
+    if (!src.in_arena) {  // small raw input: convert to word form on the device
+        PJob j;
+        j.type = JOB_REDUCE; j.src = src; j.dst = arena_alloc(n); j.n_in = n;
+        j.level = uint32_t(level); j.nlev = 0; j.raw = raw ? 1 : 0;
+        add_job(s++, j);
+        src.in_arena = true; src.off = j.dst;
+    }
+    // n > kHandoff can only remain if level == depth_target, which means n == 1 by the limit check upstream
+    std::vector<uint32_t> nodes;
+    for (uint64_t i = 0; i < n; i++) nodes.push_back(uint32_t(src.off + i));
+    return merkle_small(nodes, level, depth_target);
+}
+uint32_t SszPlan::wide_chunks(uint64_t field_off, uint64_t n_chunks, int depth_target) {
+    PSrc s; s.in_arena = false; s.off = field_off;
+    return wide_nodes(s, true, n_chunks, 0, depth_target, 0);
+}
+uint32_t SszPlan::wide_records(uint32_t type, uint64_t field_off, uint64_t n, int depth_target) {
+    if (n == 0) return zero(depth_target);
+    PJob j;
+    j.type = type; j.src.in_arena = false; j.src.off = field_off; j.dst = arena_alloc(n); j.n_in = n;
+    if (type == JOB_VALIDATORS) validator_jobs_.push_back(j); else add_job(0, j);
+    PSrc s; s.in_arena = true; s.off = j.dst;
+    return wide_nodes(s, false, n, 0, depth_target, 1);
+}
+uint32_t SszPlan::wide_pubkeys_with_extra(uint64_t field_off, uint64_t n, int depth_target, uint32_t* extra) {
+    PJob j;
+    j.type = JOB_PUBKEY48; j.src.in_arena = false; j.src.off = field_off; j.dst = arena_alloc(n + 1); j.n_in = n + 1;
+    add_job(0, j);
+    *extra = uint32_t(j.dst + n);
+    PSrc s; s.in_arena = true; s.off = j.dst;
+    return wide_nodes(s, false, n, 0, depth_target, 1);
+}
+uint64_t SszPlan::h2d_bytes() const {
+    uint64_t b = small_words_.size() * 4 + ops_.size() * sizeof(FinOp);
+    for (auto& c : copies_) b += c.nbytes;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------ execution
+int32_t ensure_zero_nodes(Engine& e) {
+    if (e.d_zero) return B200_SUCCESS;
+    // zero[i+1] = H(zero[i], zero[i]) computed on the device with the finisher (64 one-op waves)
+    uint32_t* d = nullptr;
+    B200_CUDA_TRY(cudaMalloc(&d, 65 * 32));
+    B200_CUDA_TRY(cudaMemsetAsync(d, 0, 65 * 32, e.stream));
+    std::vector<FinOp> ops(64);
+    std::vector<uint32_t> wend(64);
+    for (uint32_t i = 0; i < 64; i++) { ops[i] = FinOp{i, i, i + 1, 0}; wend[i] = i + 1; }
+    FinOp* dops = nullptr; uint32_t* dw = nullptr;
+    B200_CUDA_TRY(cudaMalloc(&dops, sizeof(FinOp) * 64));
+    B200_CUDA_TRY(cudaMalloc(&dw, 4 * 64));
+    B200_CUDA_TRY(cudaMemcpyAsync(dops, ops.data(), sizeof(FinOp) * 64, cudaMemcpyHostToDevice, e.stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(dw, wend.data(), 4 * 64, cudaMemcpyHostToDevice, e.stream));
+    launch_finisher(d, dops, dw, 64, e.stream);
+    e.launches++;
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    cudaFree(dops); cudaFree(dw);
+    e.d_zero = d;
+    return B200_SUCCESS;
+}
+
+int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, bool fields_resident,
+                     const std::vector<uint32_t>& outputs, uint8_t* out) {
+    if (small_words_.size() / 8 > kSmallCap) { e.last_error = "ssz plan: too many small leaves"; return B200_ERR_BAD_ARG; }
+    int32_t rc = ensure_zero_nodes(e);
+    if (rc) return rc;
+    B200_CUDA_TRY(arena.reserve(arena_next_ * 32));
+    B200_CUDA_TRY(fields.reserve(field_next_ + 256));
+    uint32_t* d_arena = static_cast<uint32_t*>(arena.p);
+    uint8_t* d_fields = static_cast<uint8_t*>(fields.p);
+
+    // order finisher ops by wave
+    int nwaves = 0;
+    for (int w : op_wave_) nwaves = std::max(nwaves, w + 1);
+    std::vector<uint32_t> order(ops_.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = uint32_t(i);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return op_wave_[a] < op_wave_[b]; });
+    std::vector<uint32_t> wave_end(size_t(nwaves), 0);
+    for (size_t i = 0; i < order.size(); i++) wave_end[size_t(op_wave_[order[i]])] = uint32_t(i + 1);
+    for (int w = 1; w < nwaves; w++) wave_end[size_t(w)] = std::max(wave_end[size_t(w)], wave_end[size_t(w - 1)]);
+
+    // pinned staging image: [small words | ops | wave_end | out(32 B x outputs)]
+    size_t sz_small = small_words_.size() * 4;
+    size_t sz_ops = ops_.size() * sizeof(FinOp);
+    size_t sz_wend = wave_end.size() * 4;
+    size_t off_ops = (sz_small + 15) & ~size_t(15);
+    size_t off_wend = off_ops + ((sz_ops + 15) & ~size_t(15));
+    size_t off_out = off_wend + ((sz_wend + 15) & ~size_t(15));
+    size_t total = off_out + 32 * outputs.size();
+    B200_CUDA_TRY(e.staging.reserve(total));
+    B200_CUDA_TRY(planbuf.reserve(off_out + 64));
+    uint8_t* st = static_cast<uint8_t*>(e.staging.p);
+    if (sz_small) memcpy(st, small_words_.data(), sz_small);
+    FinOp* hops = reinterpret_cast<FinOp*>(st + off_ops);
+    for (size_t i = 0; i < order.size(); i++) hops[i] = ops_[order[i]];
+    if (sz_wend) memcpy(st + off_wend, wave_end.data(), sz_wend);
+
+    cudaStream_t s = e.stream;
+    if (!fields_resident)
+        for (auto& c : copies_) {
+            B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off, c.src, c.nbytes, cudaMemcpyHostToDevice, s));
+            if (c.nbytes % 32)
+                B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, s));
+        }
+    B200_CUDA_TRY(cudaMemcpyAsync(d_arena, e.d_zero, 65 * 32, cudaMemcpyDeviceToDevice, s));
+    if (sz_small) B200_CUDA_TRY(cudaMemcpyAsync(d_arena + kSmallBase * 8, st, sz_small, cudaMemcpyHostToDevice, s));
+    uint8_t* d_plan = static_cast<uint8_t*>(planbuf.p);
+    if (sz_ops + sz_wend)
+        B200_CUDA_TRY(cudaMemcpyAsync(d_plan + off_ops, st + off_ops, off_out - off_ops, cudaMemcpyHostToDevice, s));
+
+    B200_CUDA_TRY(cudaEventRecord(e.ev0, s));
+    auto materialize = [&](const PJob& pj) {
+        Job j{};
+        j.src = pj.src.in_arena ? static_cast<const void*>(d_arena + pj.src.off * 8)
+                                : static_cast<const void*>(d_fields + pj.src.off);
+        j.dst = d_arena + pj.dst * 8;
+        j.n_in = pj.n_in; j.type = pj.type; j.level = pj.level; j.nlev = pj.nlev; j.raw = pj.raw;
+        return j;
+    };
+    for (auto& pj : validator_jobs_) { launch_validators(materialize(pj), s); e.launches++; }
+    for (auto& stage : stages_) {
+        // split into launches of at most kMaxJobsPerStage jobs
+        for (size_t b = 0; b < stage.size(); b += kMaxJobsPerStage) {
+            StageDesc sd{};
+            sd.zero_nodes = d_arena;
+            uint32_t nb = 0;
+            size_t eidx = std::min(stage.size(), b + kMaxJobsPerStage);
+            for (size_t k = b; k < eidx; k++) {
+                Job j = materialize(stage[k]);
+                uint64_t work = (j.type == JOB_REDUCE) ? ((j.n_in + (uint64_t(1) << j.nlev) - 1) >> j.nlev) : j.n_in;
+                j.block_begin = nb;
+                nb += uint32_t((work + kStageThreads - 1) / kStageThreads);
+                sd.jobs[sd.njobs++] = j;
+            }
+            sd.nblocks = nb;
+            launch_stage(sd, s);
+            e.launches++;
+        }
+    }
+    if (nwaves) {
+        launch_finisher(d_arena, reinterpret_cast<const FinOp*>(d_plan + off_ops),
+                        reinterpret_cast<const uint32_t*>(d_plan + off_wend), nwaves, s);
+        e.launches++;
+    }
+    B200_CUDA_TRY(cudaEventRecord(e.ev1, s));
+    B200_CUDA_TRY(cudaGetLastError());
+    for (size_t i = 0; i < outputs.size(); i++)
+        B200_CUDA_TRY(cudaMemcpyAsync(st + off_out + 32 * i, d_arena + uint64_t(outputs[i]) * 8, 32,
+                                      cudaMemcpyDeviceToHost, s));
+    B200_CUDA_TRY(cudaStreamSynchronize(s));
+    B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, e.ev0, e.ev1));
+    for (size_t i = 0; i < outputs.size(); i++) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(st + off_out + 32 * i);
+        for (int k = 0; k < 8; k++) {
+            out[32 * i + 4 * k + 0] = uint8_t(w[k] >> 24); out[32 * i + 4 * k + 1] = uint8_t(w[k] >> 16);
+            out[32 * i + 4 * k + 2] = uint8_t(w[k] >> 8);  out[32 * i + 4 * k + 3] = uint8_t(w[k]);
+        }
+    }
+    return B200_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------ BeaconState
+namespace {
+struct Preset {
+    uint64_t slots_per_historical_root, historical_roots_limit, eth1_data_votes_bound, validator_registry_limit,
+        epochs_per_historical_vector, epochs_per_slashings_vector, sync_committee_size;
+};
+// /root/reference/ethereum-consensus/src/phase0/presets/{mainnet.rs:5-36,82-83, minimal.rs:20-25},
+// altair/presets/{mainnet,minimal}.rs:19
+const Preset kPresets[2] = {
+    {8192, 1ull << 24, 2048, 1ull << 40, 65536, 8192, 512},
+    {64, 1ull << 24, 32, 1ull << 40, 64, 64, 32},
+};
+inline uint32_t le32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (uint32_t(p[3]) << 24); }
+inline uint64_t le64(const uint8_t* p) { return uint64_t(le32(p)) | (uint64_t(le32(p + 4)) << 32); }
+}  // namespace
+
+bool parse_beacon_state(const uint8_t* s, size_t len, int preset, StateOffsets& so) {
+    if (preset < 0 || preset > 1) return false;
+    const Preset& P = kPresets[preset];
+    size_t fixed = 8 + 32 + 8 + 16 + 112 + 2 * 32 * P.slots_per_historical_root + 4 + 72 + 4 + 8 + 4 + 4 +
+                   32 * P.epochs_per_historical_vector + 8 * P.epochs_per_slashings_vector + 4 + 4 + 1 + 3 * 40 + 4 +
+                   2 * (48 * P.sync_committee_size + 48) + 4 + 8 + 8 + 4;
+    if (len < fixed || len > 0xffffffffull) return false;
+    size_t o = 8 + 32 + 8 + 16 + 112;
+    so.block_roots = o; o += 32 * P.slots_per_historical_root;
+    so.state_roots = o; o += 32 * P.slots_per_historical_root;
+    so.var[0] = le32(s + o); o += 4;  // historical_roots
+    so.eth1_data = o; o += 72;
+    so.var[1] = le32(s + o); o += 4;  // eth1_data_votes
+    so.eth1_deposit_index = o; o += 8;
+    so.var[2] = le32(s + o); o += 4;  // validators
+    so.var[3] = le32(s + o); o += 4;  // balances
+    so.randao_mixes = o; o += 32 * P.epochs_per_historical_vector;
+    so.slashings = o; o += 8 * P.epochs_per_slashings_vector;
+    so.var[4] = le32(s + o); o += 4;  // previous_epoch_participation
+    so.var[5] = le32(s + o); o += 4;  // current_epoch_participation
+    so.justification_bits = o; o += 1;
+    so.checkpoints = o; o += 120;
+    so.var[6] = le32(s + o); o += 4;  // inactivity_scores
+    so.current_sync_committee = o; o += 48 * P.sync_committee_size + 48;
+    so.next_sync_committee = o; o += 48 * P.sync_committee_size + 48;
+    so.var[7] = le32(s + o); o += 4;  // latest_execution_payload_header
+    so.next_withdrawal_index = o; o += 8;
+    so.next_withdrawal_validator_index = o; o += 8;
+    so.var[8] = le32(s + o); o += 4;  // historical_summaries
+    so.var[9] = uint32_t(len);
+    so.fixed = fixed;
+    if (o != fixed || so.var[0] != fixed) return false;
+    for (int i = 0; i < 9; i++)
+        if (so.var[i] > so.var[i + 1]) return false;
+    auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
+    if (sz(0) % 32 || sz(1) % 72 || sz(1) / 72 > P.eth1_data_votes_bound || sz(2) % 121 || sz(3) % 8 || sz(6) % 8 ||
+        sz(8) % 64 || sz(0) / 32 > P.historical_roots_limit || sz(8) / 64 > P.historical_roots_limit)
+        return false;
+    // ExecutionPayloadHeader: 584-byte fixed part whose only offset (extra_data) must equal 584; <= 32 bytes extra
+    if (sz(7) < 584 || sz(7) > 584 + 32) return false;
+    if (le32(s + so.var[7] + 436) != 584) return false;
+    return true;
+}
+
+// Everything except the five big lists; `big[5]` = their roots (already length-mixed).
+static uint32_t assemble_state(SszPlan& p, const uint8_t* s, const StateOffsets& so, const Preset& P,
+                               const uint32_t big[5]) {
+    std::vector<uint32_t> f(28);
+    auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
+    f[0] = p.leaf_bytes(s + 0, 8);
+    f[1] = p.leaf(s + 8);
+    f[2] = p.leaf_bytes(s + 40, 8);
+    f[3] = p.container({p.leaf_bytes(s + 48, 4), p.leaf_bytes(s + 52, 4), p.leaf_bytes(s + 56, 8)});
+    f[4] = p.container({p.leaf_bytes(s + 64, 8), p.leaf_bytes(s + 72, 8), p.leaf(s + 80), p.leaf(s + 112), p.leaf(s + 144)});
+    int d_hist = depth_for(P.slots_per_historical_root);
+    f[5] = p.wide_chunks(p.stage_field(s + so.block_roots, 32 * P.slots_per_historical_root), P.slots_per_historical_root, d_hist);
+    f[6] = p.wide_chunks(p.stage_field(s + so.state_roots, 32 * P.slots_per_historical_root), P.slots_per_historical_root, d_hist);
+    f[7] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[0], sz(0)), sz(0) / 32, depth_for(P.historical_roots_limit)), sz(0) / 32);
+    {
+        const uint8_t* e = s + so.eth1_data;
+        f[8] = p.container({p.leaf(e), p.leaf_bytes(e + 32, 8), p.leaf(e + 40)});
+    }
+    f[9] = p.mix_in_length(p.wide_records(JOB_ETH1DATA, p.stage_field(s + so.var[1], sz(1)), sz(1) / 72, depth_for(P.eth1_data_votes_bound)), sz(1) / 72);
+    f[10] = p.leaf_bytes(s + so.eth1_deposit_index, 8);
+    f[11] = big[0];
+    f[12] = big[1];
+    f[13] = p.wide_chunks(p.stage_field(s + so.randao_mixes, 32 * P.epochs_per_historical_vector), P.epochs_per_historical_vector, depth_for(P.epochs_per_historical_vector));
+    f[14] = p.wide_chunks(p.stage_field(s + so.slashings, 8 * P.epochs_per_slashings_vector), P.epochs_per_slashings_vector / 4, depth_for(P.epochs_per_slashings_vector / 4));
+    f[15] = big[2];
+    f[16] = big[3];
+    f[17] = p.leaf_bytes(s + so.justification_bits, 1);
+    for (int i = 0; i < 3; i++) {
+        const uint8_t* c = s + so.checkpoints + 40 * i;
+        f[18 + i] = p.hash2(p.leaf_bytes(c, 8), p.leaf(c + 8));
+    }
+    f[21] = big[4];
+    for (int k = 0; k < 2; k++) {
+        const uint8_t* c = s + (k == 0 ? so.current_sync_committee : so.next_sync_committee);
+        size_t n = P.sync_committee_size;
+        // pubkeys vector and the aggregate key share one staged region: n + 1 records, hashed by one PUBKEY48 job
+        uint64_t off = p.stage_field(c, 48 * (n + 1));
+        uint32_t agg;
+        uint32_t keys = p.wide_pubkeys_with_extra(off, n, depth_for(n), &agg);
+        f[22 + k] = p.hash2(keys, agg);
+    }
+    {
+        const uint8_t* h = s + so.var[7];
+        size_t hl = sz(7);
+        std::vector<uint32_t> l(17);
+        l[0] = p.leaf(h + 0);
+        l[1] = p.leaf_bytes(h + 32, 20);
+        l[2] = p.leaf(h + 52);
+        l[3] = p.leaf(h + 84);
+        std::vector<uint32_t> bloom(8);
+        for (int i = 0; i < 8; i++) bloom[i] = p.leaf(h + 116 + 32 * i);
+        l[4] = p.merkle_small(bloom, 0, 3);
+        l[5] = p.leaf(h + 372);
+        for (int i = 0; i < 4; i++) l[6 + i] = p.leaf_bytes(h + 404 + 8 * i, 8);
+        size_t extra = hl - 584;
+        std::vector<uint32_t> ex;
+        if (extra) ex.push_back(p.leaf_bytes(h + 584, extra));
+        l[10] = p.mix_in_length(p.merkle_small(ex, 0, 0), extra);
+        l[11] = p.leaf(h + 440);
+        l[12] = p.leaf(h + 472);
+        l[13] = p.leaf(h + 504);
+        l[14] = p.leaf(h + 536);
+        l[15] = p.leaf_bytes(h + 568, 8);
+        l[16] = p.leaf_bytes(h + 576, 8);
+        f[24] = p.container(l);
+    }
+    f[25] = p.leaf_bytes(s + so.next_withdrawal_index, 8);
+    f[26] = p.leaf_bytes(s + so.next_withdrawal_validator_index, 8);
+    f[27] = p.mix_in_length(p.wide_records(JOB_PAIR64, p.stage_field(s + so.var[8], sz(8)), sz(8) / 64, depth_for(P.historical_roots_limit)), sz(8) / 64);
+    return p.container(f);
+}
+
+// slice [rank*S, (rank+1)*S) of a list whose dense part is split into `world` subtrees of 2^k leaves
+static void slice_of(uint64_t n, int world, int rank, uint64_t* first, uint64_t* count, int* k) {
+    uint64_t per = (n + uint64_t(world) - 1) / uint64_t(world);
+    int kk = depth_for(per ? per : 1);
+    uint64_t S = uint64_t(1) << kk;
+    uint64_t lo = std::min(n, S * uint64_t(rank)), hi = std::min(n, S * uint64_t(rank + 1));
+    *first = lo; *count = hi - lo; *k = kk;
+}
+
+int32_t build_beacon_state_plan(SszPlan& p, const uint8_t* s, size_t len, int preset, std::vector<uint32_t>& outputs) {
+    StateOffsets so;
+    if (!parse_beacon_state(s, len, preset, so)) return B200_ERR_SSZ_MALFORMED;
+    const Preset& P = kPresets[preset];
+    auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
+    uint32_t big[5];
+    int d_reg = depth_for(P.validator_registry_limit);
+    big[0] = p.mix_in_length(p.wide_records(JOB_VALIDATORS, p.stage_field(s + so.var[2], sz(2)), sz(2) / 121, d_reg), sz(2) / 121);
+    big[1] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[3], sz(3)), (sz(3) + 31) / 32, d_reg - 2), sz(3) / 8);
+    big[2] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[4], sz(4)), (sz(4) + 31) / 32, d_reg - 5), sz(4));
+    big[3] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[5], sz(5)), (sz(5) + 31) / 32, d_reg - 5), sz(5));
+    big[4] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[6], sz(6)), (sz(6) + 31) / 32, d_reg - 2), sz(6) / 8);
+    outputs.assign(1, assemble_state(p, s, so, P, big));
+    return B200_SUCCESS;
+}
+
+int32_t build_beacon_state_shard_plan(SszPlan& p, const uint8_t* s, size_t len, int preset, int rank, int world,
+                                      std::vector<uint32_t>& outputs) {
+    StateOffsets so;
+    if (!parse_beacon_state(s, len, preset, so)) return B200_ERR_SSZ_MALFORMED;
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return B200_ERR_BAD_ARG;
+    auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
+    outputs.clear();
+    uint64_t first, count; int k;
+    // validators: records
+    slice_of(sz(2) / 121, world, rank, &first, &count, &k);
+    outputs.push_back(p.wide_records(JOB_VALIDATORS, p.stage_field(s + so.var[2] + 121 * first, 121 * count), count, k));
+    // packed lists: chunk-granular slices (slice starts are multiples of 2^k chunks => 32-byte aligned)
+    const int idx[4] = {3, 4, 5, 6};
+    for (int q = 0; q < 4; q++) {
+        size_t nb = sz(idx[q]);
+        uint64_t nch = (nb + 31) / 32;
+        slice_of(nch, world, rank, &first, &count, &k);
+        size_t b0 = size_t(first) * 32, b1 = std::min(nb, size_t(first + count) * 32);
+        outputs.push_back(p.wide_chunks(p.stage_field(s + so.var[idx[q]] + b0, b1 - b0), count, k));
+    }
+    return B200_SUCCESS;
+}
+
+int32_t build_beacon_state_combine_plan(SszPlan& p, const uint8_t* s, size_t len, int preset, int world,
+                                        const uint8_t* all_roots, std::vector<uint32_t>& outputs) {
+    StateOffsets so;
+    if (!parse_beacon_state(s, len, preset, so)) return B200_ERR_SSZ_MALFORMED;
+    if (world < 1 || (world & (world - 1))) return B200_ERR_BAD_ARG;
+    const Preset& P = kPresets[preset];
+    auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
+    int d_reg = depth_for(P.validator_registry_limit);
+    const uint64_t n_elems[5] = {sz(2) / 121, (sz(3) + 31) / 32, (sz(4) + 31) / 32, (sz(5) + 31) / 32, (sz(6) + 31) / 32};
+    const uint64_t lens[5] = {sz(2) / 121, sz(3) / 8, sz(4), sz(5), sz(6) / 8};
+    const int depth[5] = {d_reg, d_reg - 2, d_reg - 5, d_reg - 5, d_reg - 2};
+    uint32_t big[5];
+    for (int q = 0; q < 5; q++) {
+        uint64_t first, count; int k;
+        slice_of(n_elems[q], world, 0, &first, &count, &k);
+        std::vector<uint32_t> nodes;
+        for (int r = 0; r < world; r++) nodes.push_back(p.leaf(all_roots + (size_t(r) * 5 + q) * 32));
+        big[q] = p.mix_in_length(p.merkle_small(nodes, k, depth[q]), lens[q]);
+    }
+    outputs.assign(1, assemble_state(p, s, so, P, big));
+    return B200_SUCCESS;
+}
+
+}  // namespace b200

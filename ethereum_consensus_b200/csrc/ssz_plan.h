@@ -1,0 +1,117 @@
+// Host-side planner for SSZ hash_tree_root on the device: turns a container instance into
+//   (a) H2D copies of its big fields into 256-byte-aligned device regions,
+//   (b) wide stage launches (ssz_kernels.cu) over those regions,
+//   (c) a finisher op list for everything small (tops of trees, zero-hash chains, mix-ins, small containers).
+// The planner does no hashing itself; all SHA-256 work happens on the device.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "engine.h"
+#include "ssz_kernels.cuh"
+
+namespace b200 {
+
+// source of a wide job: either a region of the field buffer (raw SSZ bytes) or nodes in the arena
+struct PSrc {
+    bool in_arena = false;
+    uint64_t off = 0;  // byte offset in the field buffer, or node index in the arena
+};
+
+struct PJob {
+    uint32_t type = JOB_REDUCE;
+    PSrc src;
+    uint64_t dst = 0;  // node index in the arena
+    uint64_t n_in = 0;
+    uint32_t level = 0, nlev = 0, raw = 0;
+};
+
+struct HostCopy {
+    const uint8_t* src;
+    size_t nbytes;
+    uint64_t field_off;
+    size_t zero_tail;  // bytes to clear after the copy (keeps the last partial chunk zero-padded)
+};
+
+class SszPlan {
+public:
+    static constexpr uint32_t kZeroBase = 0;   // arena[0..65) = zero-subtree hashes
+    static constexpr uint64_t kHandoff = 64;   // <= this many nodes: finish in the single-CTA finisher
+
+    SszPlan() = default;
+
+    // ---- building blocks (return arena node indices) ----
+    uint32_t zero(int depth) const { return kZeroBase + uint32_t(depth); }
+    uint32_t leaf(const uint8_t chunk[32]);              // small leaf uploaded with the plan
+    uint32_t leaf_u64(uint64_t v);
+    uint32_t leaf_bytes(const uint8_t* p, size_t n);     // n <= 32, right-padded
+    uint32_t hash2(uint32_t a, uint32_t b);              // finisher op
+    uint32_t mix_in_length(uint32_t root, uint64_t len) { return hash2(root, leaf_u64(len)); }
+    // root (at `depth_target`) of explicit nodes sitting at `level`
+    uint32_t merkle_small(std::vector<uint32_t> nodes, int level, int depth_target);
+    // container of small field roots
+    uint32_t container(const std::vector<uint32_t>& field_roots);
+    // stage a host region into the field buffer (16-byte padded, 256-byte aligned)
+    uint64_t stage_field(const uint8_t* src, size_t nbytes);
+    // root at depth_target of `n` chunks/records living in the field buffer
+    uint32_t wide_chunks(uint64_t field_off, uint64_t n_chunks, int depth_target);
+    uint32_t wide_records(uint32_t type, uint64_t field_off, uint64_t n, int depth_target);
+    // generic: n nodes at `level`, located at src, reduced to depth_target starting at stage `s`
+    uint32_t wide_nodes(PSrc src, bool raw, uint64_t n, int level, int depth_target, size_t s);
+
+    // n+1 48-byte records (n vector elements + 1 extra key) hashed by one job; returns the vector root
+    uint32_t wide_pubkeys_with_extra(uint64_t field_off, uint64_t n, int depth_target, uint32_t* extra);
+
+    // ---- execution ----
+    // Uploads fields (+plan) and runs; `fields_resident`: skip the field H2D copies (device-resident state).
+    // `outputs`: arena nodes to read back (32 bytes each, SSZ byte order) into `out`.
+    int32_t run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, bool fields_resident,
+                const std::vector<uint32_t>& outputs, uint8_t* out);
+
+    size_t field_bytes() const { return field_next_; }
+    uint64_t arena_nodes() const { return arena_next_; }
+    uint64_t h2d_bytes() const;
+
+private:
+    uint64_t arena_alloc(uint64_t n) { uint64_t r = arena_next_; arena_next_ += n; return r; }
+    void add_job(size_t stage, const PJob& j);
+
+    std::vector<PJob> validator_jobs_;
+    std::vector<std::vector<PJob>> stages_;
+    std::vector<FinOp> ops_;
+    std::vector<int> op_wave_;
+    std::unordered_map<uint32_t, int> ready_;  // finisher-produced node -> first wave in which it is readable
+    std::vector<uint32_t> small_words_; // word-form image of small leaves
+    std::vector<uint32_t> small_idx_;   // arena idx of each small leaf
+    std::vector<HostCopy> copies_;
+    uint64_t arena_next_ = 65 + 8192;  // [0,65) zero hashes, [65, 65+8192) small leaves uploaded with the plan
+    size_t field_next_ = 0;
+
+    int ready_wave(uint32_t idx) const;
+};
+
+int depth_for(uint64_t n);
+
+// deneb BeaconState (/root/reference/ethereum-consensus/src/deneb/beacon_state.rs:26-63): byte offsets of the
+// fixed-size fields and of the nine variable-size fields inside the SSZ serialization.
+struct StateOffsets {
+    size_t fixed = 0;
+    size_t block_roots = 0, state_roots = 0, eth1_data = 0, eth1_deposit_index = 0, randao_mixes = 0, slashings = 0,
+           justification_bits = 0, checkpoints = 0, current_sync_committee = 0, next_sync_committee = 0,
+           next_withdrawal_index = 0, next_withdrawal_validator_index = 0;
+    // historical_roots, eth1_data_votes, validators, balances, previous/current participation, inactivity_scores,
+    // latest_execution_payload_header, historical_summaries, end
+    uint32_t var[10] = {0};
+};
+bool parse_beacon_state(const uint8_t* ssz, size_t len, int preset, StateOffsets& so);
+int32_t build_beacon_state_plan(SszPlan& plan, const uint8_t* ssz, size_t len, int preset, std::vector<uint32_t>& outputs);
+int32_t build_beacon_state_shard_plan(SszPlan& plan, const uint8_t* ssz, size_t len, int preset, int rank, int world,
+                                      std::vector<uint32_t>& outputs);
+int32_t build_beacon_state_combine_plan(SszPlan& plan, const uint8_t* ssz, size_t len, int preset, int world,
+                                        const uint8_t* all_roots, std::vector<uint32_t>& outputs);
+
+int32_t ensure_zero_nodes(Engine& e);
+
+}  // namespace b200

@@ -1,0 +1,109 @@
+/*
+ * b200_consensus.h — C ABI of the B200-native batch-crypto engine.
+ *
+ * This is the drop-in boundary for ralexstokes/ethereum_consensus' hot path:
+ *   - BLS:  the seven free functions re-exported at
+ *           /root/reference/ethereum-consensus/src/crypto/mod.rs:4-8 (bodies in crypto/bls.rs:64-160), whose only
+ *           backend today is `use blst::{min_pk as bls_impl, BLST_ERROR}` (crypto/bls.rs:4);
+ *   - SSZ:  `HashTreeRoot::hash_tree_root` / `merkleize` / `is_valid_merkle_branch` from
+ *           `pub use ssz_rs::prelude::*` (/root/reference/ethereum-consensus/src/ssz/mod.rs:6).
+ * Plain pointers and sizes only; the caller owns every buffer; calls are synchronous and thread-safe (one
+ * process-global context per device).  INTEGRATION.md shows the Rust `extern "C"` block that binds these.
+ *
+ * Return codes: 0..7 are blst's BLST_ERROR values (order pinned by
+ * /root/reference/ethereum-consensus/src/crypto/bls.rs:48-62); >= 0x100 are engine failures (CUDA, bad
+ * arguments, malformed SSZ) and are NEVER conflated with a signature verdict.  There is no CPU fallback: if
+ * the device or the CUDA library is unavailable every entry point returns B200_ERR_NO_DEVICE / B200_ERR_CUDA.
+ */
+#ifndef B200_CONSENSUS_H
+#define B200_CONSENSUS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes -------------------------------------------------------------------------------- */
+enum {
+    B200_SUCCESS = 0,            /* BLST_SUCCESS */
+    B200_BAD_ENCODING = 1,       /* BLST_BAD_ENCODING */
+    B200_POINT_NOT_ON_CURVE = 2, /* BLST_POINT_NOT_ON_CURVE */
+    B200_POINT_NOT_IN_GROUP = 3, /* BLST_POINT_NOT_IN_GROUP */
+    B200_AGGR_TYPE_MISMATCH = 4, /* BLST_AGGR_TYPE_MISMATCH */
+    B200_VERIFY_FAIL = 5,        /* BLST_VERIFY_FAIL  -> Error::InvalidSignature (crypto/bls.rs:127-131) */
+    B200_PK_IS_INFINITY = 6,     /* BLST_PK_IS_INFINITY */
+    B200_BAD_SCALAR = 7,         /* BLST_BAD_SCALAR */
+    B200_EMPTY_AGGREGATE = 16,   /* Error::EmptyAggregate (crypto/bls.rs:80-82,136-138) */
+    B200_ERR_CUDA = 0x100,
+    B200_ERR_NO_DEVICE = 0x101,
+    B200_ERR_BAD_ARG = 0x102,
+    B200_ERR_SSZ_MALFORMED = 0x103, /* offsets / lengths inconsistent with the container schema */
+    B200_ERR_NOT_INITIALIZED = 0x104,
+    B200_ERR_LIMIT = 0x105          /* more chunks than the declared limit (MerkleizationError) */
+};
+
+enum { B200_PRESET_MAINNET = 0, B200_PRESET_MINIMAL = 1 };
+
+/* ---- life cycle ------------------------------------------------------------------------------------ */
+/* Binds the calling process to CUDA device `device` (one process per GPU).  Idempotent. */
+B200_API int32_t b200_init(int32_t device);
+B200_API void b200_shutdown(void);
+/* Human-readable text for the last engine failure (>= 0x100) on this thread's context. */
+B200_API const char* b200_last_error(void);
+/* Number of kernel launches issued by the library since b200_init (bench.py's gpu_launches). */
+B200_API uint64_t b200_launch_count(void);
+/* Device time (ms, CUDA events on the library stream) of the kernels of the last SSZ / BLS call. */
+B200_API float b200_last_kernel_ms(void);
+
+/* ---- SSZ / SHA-256 Merkle (replaces ssz_rs merkleize / hash_tree_root; sha2 one-shot) -------------- */
+/* crypto::hash — /root/reference/ethereum-consensus/src/crypto/bls.rs:12-20 (computed on the device). */
+B200_API int32_t b200_sha256(const uint8_t* data, size_t len, uint8_t out[32]);
+
+/* merkleize(chunks, limit): `n_chunks` 32-byte chunks, virtually zero-padded to `limit` chunks
+ * (limit == 0: next power of two of n_chunks).  ssz_rs `merkleize`. */
+B200_API int32_t b200_merkleize(const uint8_t* chunks, size_t n_chunks, uint64_t limit, uint8_t out[32]);
+/* mix_in_length(root, len) */
+B200_API int32_t b200_mix_in_length(const uint8_t root[32], uint64_t length, uint8_t out[32]);
+/* is_valid_merkle_branch(leaf, branch[depth], depth, index, root): *ok = 1/0.
+ * Used at /root/reference/ethereum-consensus/src/phase0/block_processing.rs:428-437 and deneb/blob_sidecar.rs:58-63. */
+B200_API int32_t b200_is_valid_merkle_branch(const uint8_t leaf[32], const uint8_t* branch, size_t depth, uint64_t index,
+                                    const uint8_t root[32], int32_t* ok);
+
+/* hash_tree_root(List<Validator, limit>) from N x 121 bytes of SSZ (phase0/validator.rs:10-26). */
+B200_API int32_t b200_htr_validators(const uint8_t* ssz, size_t n, uint64_t limit, uint8_t out[32]);
+/* hash_tree_root of a packed basic List (is_list=1, mixes `length`) or Vector (is_list=0):
+ * `nbytes` of little-endian elements, limit in chunks. */
+B200_API int32_t b200_htr_packed(const uint8_t* data, size_t nbytes, uint64_t limit_chunks, int32_t is_list, uint64_t length,
+                        uint8_t out[32]);
+
+/* hash_tree_root(deneb::BeaconState) from its SSZ serialization
+ * (/root/reference/ethereum-consensus/src/deneb/beacon_state.rs:13-64; called at deneb/spec/mod.rs:3215,3288). */
+B200_API int32_t b200_htr_beacon_state_deneb(const uint8_t* ssz, size_t len, int32_t preset, uint8_t out[32]);
+
+/* Device-resident state: upload once, re-hash many times (kernel-only cost; SURVEY.md §8f-2 groundwork). */
+typedef struct b200_state b200_state;
+B200_API int32_t b200_state_upload_deneb(const uint8_t* ssz, size_t len, int32_t preset, b200_state** out_handle);
+B200_API int32_t b200_state_root(b200_state* handle, uint8_t out[32]);
+B200_API void b200_state_free(b200_state* handle);
+
+/* Multi-GPU sharding of hash_tree_root(BeaconState): rank r of `world` hashes its contiguous
+ * power-of-two-aligned slice of the five big lists and returns one subtree root per list
+ * (out_roots: 5 x 32 bytes, order validators, balances, previous/current participation, inactivity_scores);
+ * after an allgather of those roots, b200_htr_beacon_state_deneb_combine finishes the tree on any rank. */
+B200_API int32_t b200_htr_beacon_state_deneb_shard(const uint8_t* ssz, size_t len, int32_t preset, int32_t rank, int32_t world,
+                                          uint8_t* out_roots /* 5*32 */);
+B200_API int32_t b200_htr_beacon_state_deneb_combine(const uint8_t* ssz, size_t len, int32_t preset, int32_t world,
+                                            const uint8_t* all_roots /* world*5*32 */, uint8_t out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_CONSENSUS_H */

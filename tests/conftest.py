@@ -1,0 +1,45 @@
+import ctypes
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def _make_oracles():
+    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True, capture_output=True)
+
+
+@pytest.fixture(scope="session")
+def oracle_ssz_c():
+    """The plain-C SSZ oracle (oracle/c/ssz_oracle.c) loaded through ctypes."""
+    _make_oracles()
+    lib = ctypes.CDLL(str(ROOT / "oracle" / "liboracle_ssz.so"))
+    V, S, U64, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int
+    lib.orc_sha256.argtypes = [V, S, V]
+    lib.orc_merkleize.argtypes = [V, S, U64, I, V]
+    lib.orc_merkleize.restype = I
+    lib.orc_htr_packed.argtypes = [V, S, U64, I, U64, I, V]
+    lib.orc_htr_validators.argtypes = [V, S, U64, I, V]
+    lib.orc_htr_beacon_state_deneb.argtypes = [V, S, I, I, V]
+    lib.orc_htr_beacon_state_deneb.restype = I
+    lib.orc_validator_root.argtypes = [V, V]
+    lib.orc_mix_in_length.argtypes = [V, U64, V]
+    lib.orc_hash_pairs.argtypes = [V, S, I, V]
+    return lib
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """The CUDA library bound to cuda:0 — fails loudly (no CPU fallback) if it cannot initialise."""
+    from ethereum_consensus_b200 import _lib
+    return _lib.init(int(os.environ.get("LOCAL_RANK", "0")))
