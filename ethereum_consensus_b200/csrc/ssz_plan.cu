@@ -420,7 +420,7 @@ int32_t build_beacon_state_shard_plan(SszPlan& p, const uint8_t* s, size_t len, 
         size_t nb = sz(idx[q]);
         uint64_t nch = (nb + 31) / 32;
         slice_of(nch, world, rank, &first, &count, &k);
-        size_t b0 = size_t(first) * 32, b1 = std::min(nb, size_t(first + count) * 32);
+        size_t b0 = std::min(nb, size_t(first) * 32), b1 = std::min(nb, size_t(first + count) * 32);
         outputs.push_back(p.wide_chunks(p.stage_field(s + so.var[idx[q]] + b0, b1 - b0), count, k));
     }
     return B200_SUCCESS;
