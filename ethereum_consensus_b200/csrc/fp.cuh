@@ -1,0 +1,225 @@
+// Fp: the BLS12-381 base field, 381-bit, 12 x 32-bit limbs kept in registers, Montgomery form (R = 2^384).
+//
+// This is the arithmetic blst implements in x86-64 assembly for the reference
+// (/root/reference/ethereum-consensus/src/crypto/bls.rs:4 `use blst::{min_pk as bls_impl, ..}`), re-designed for
+// the B200 integer pipe: a Montgomery product is 2 x 12 x 12 32x32->64 multiply-adds (IMAD.WIDE on the fma
+// pipe) plus carry propagation on the ALU pipe.  No tensor cores: this is modular integer arithmetic.
+//
+// The same source compiles for the host (`B200_HD` = inline) so that every layer above Fp (towers, curves,
+// pairing, hash-to-curve) is unit-tested on the CPU against the big-int oracle before it ever runs on a GPU;
+// the host build exists only inside tests/host_math — the product library launches kernels, nothing else.
+#pragma once
+#include <cstdint>
+
+#include "bls_consts.cuh"
+
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define B200_HD inline
+#define B200_HD_NOINLINE
+#endif
+
+namespace b200 {
+
+struct Fp {
+    uint32_t l[12];
+};
+
+B200_HD Fp fp_p() { Fp r = B200_FP_P; return r; }
+B200_HD Fp fp_zero() { Fp r = B200_FP_ZERO; return r; }
+B200_HD Fp fp_one() { Fp r = B200_FP_ONE; return r; }
+
+B200_HD bool fp_is_zero(const Fp& a) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc |= a.l[i];
+    return acc == 0;
+}
+B200_HD bool fp_eq(const Fp& a, const Fp& b) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc |= a.l[i] ^ b.l[i];
+    return acc == 0;
+}
+// a >= b as 384-bit integers
+B200_HD bool fp_geq_raw(const Fp& a, const Fp& b) {
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t d = uint64_t(a.l[i]) - b.l[i] - borrow;
+        borrow = (d >> 32) & 1;
+    }
+    return borrow == 0;
+}
+// r = a - b (mod 2^384), returns the borrow
+B200_HD uint32_t fp_sub_raw(Fp& r, const Fp& a, const Fp& b) {
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t d = uint64_t(a.l[i]) - b.l[i] - borrow;
+        r.l[i] = uint32_t(d);
+        borrow = (d >> 32) & 1;
+    }
+    return uint32_t(borrow);
+}
+B200_HD uint32_t fp_add_raw(Fp& r, const Fp& a, const Fp& b) {
+    uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t s = uint64_t(a.l[i]) + b.l[i] + carry;
+        r.l[i] = uint32_t(s);
+        carry = s >> 32;
+    }
+    return uint32_t(carry);
+}
+// conditional final subtraction: r in [0, 2p) -> [0, p)
+B200_HD void fp_reduce_once(Fp& r) {
+    const Fp p = fp_p();
+    Fp t;
+    uint32_t borrow = fp_sub_raw(t, r, p);
+    if (!borrow) r = t;
+}
+B200_HD void fp_add(Fp& r, const Fp& a, const Fp& b) {
+    fp_add_raw(r, a, b);  // p < 2^381: no carry out of 384 bits
+    fp_reduce_once(r);
+}
+B200_HD void fp_sub(Fp& r, const Fp& a, const Fp& b) {
+    const Fp p = fp_p();
+    Fp t;
+    uint32_t borrow = fp_sub_raw(t, a, b);
+    if (borrow) fp_add_raw(t, t, p);
+    r = t;
+}
+B200_HD void fp_neg(Fp& r, const Fp& a) {
+    if (fp_is_zero(a)) { r = a; return; }
+    const Fp p = fp_p();
+    fp_sub_raw(r, p, a);
+}
+B200_HD void fp_dbl(Fp& r, const Fp& a) { fp_add(r, a, a); }
+
+// Montgomery product r = a*b/R mod p (CIOS, operand scanning).  Portable C++: identical on host and device.
+B200_HD void fp_mul(Fp& r, const Fp& a, const Fp& b) {
+    const Fp p = fp_p();
+    uint32_t t[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            uint64_t cur = uint64_t(a.l[j]) * b.l[i] + t[j] + carry;
+            t[j] = uint32_t(cur);
+            carry = cur >> 32;
+        }
+        uint64_t cur = uint64_t(t[12]) + carry;
+        t[12] = uint32_t(cur);
+        t[13] = uint32_t(cur >> 32);
+        const uint32_t m = t[0] * B200_FP_N0;
+        cur = uint64_t(m) * p.l[0] + t[0];
+        carry = cur >> 32;
+#pragma unroll
+        for (int j = 1; j < 12; j++) {
+            cur = uint64_t(m) * p.l[j] + t[j] + carry;
+            t[j - 1] = uint32_t(cur);
+            carry = cur >> 32;
+        }
+        cur = uint64_t(t[12]) + carry;
+        t[11] = uint32_t(cur);
+        t[12] = t[13] + uint32_t(cur >> 32);
+    }
+    Fp out;
+#pragma unroll
+    for (int i = 0; i < 12; i++) out.l[i] = t[i];
+    fp_reduce_once(out);  // t < 2p
+    r = out;
+}
+B200_HD void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
+
+B200_HD void fp_to_mont(Fp& r, const Fp& a) { const Fp r2 = B200_FP_R2; fp_mul(r, a, r2); }
+B200_HD void fp_from_mont(Fp& r, const Fp& a) {
+    Fp one;
+#pragma unroll
+    for (int i = 0; i < 12; i++) one.l[i] = 0;
+    one.l[0] = 1;
+    fp_mul(r, a, one);
+}
+
+// 48 big-endian bytes -> raw integer limbs (no reduction, not Montgomery)
+B200_HD void fp_from_be_bytes_raw(Fp& r, const uint8_t* b) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint8_t* q = b + 44 - 4 * i;
+        r.l[i] = (uint32_t(q[0]) << 24) | (uint32_t(q[1]) << 16) | (uint32_t(q[2]) << 8) | q[3];
+    }
+}
+B200_HD void fp_to_be_bytes_raw(uint8_t* b, const Fp& a) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint8_t* q = b + 44 - 4 * i;
+        q[0] = uint8_t(a.l[i] >> 24); q[1] = uint8_t(a.l[i] >> 16); q[2] = uint8_t(a.l[i] >> 8); q[3] = uint8_t(a.l[i]);
+    }
+}
+
+// "lexicographically largest": plain integer value > (p-1)/2.  `a` in Montgomery form.
+B200_HD bool fp_is_lex_largest(const Fp& a) {
+    Fp raw;
+    fp_from_mont(raw, a);
+    const Fp half = B200_FP_HALF_P;
+    return !fp_geq_raw(half, raw);  // raw > half
+}
+// parity of the plain integer value (sgn0 building block)
+B200_HD uint32_t fp_parity(const Fp& a) {
+    Fp raw;
+    fp_from_mont(raw, a);
+    return raw.l[0] & 1;
+}
+
+// exponent tables: device code reads them from the constant bank, host code from static storage
+#if defined(__CUDACC__)
+static __constant__ uint32_t d_exp_p_minus_2[12] = B200_EXP_P_MINUS_2;
+static __constant__ uint32_t d_exp_sqrt[12] = B200_EXP_P_PLUS_1_DIV_4;
+static __constant__ uint32_t d_exp_p_minus_3_div_4[12] = B200_EXP_P_MINUS_3_DIV_4;
+static __constant__ uint32_t d_exp_p_minus_1_div_2[12] = B200_EXP_P_MINUS_1_DIV_2;
+#endif
+static const uint32_t h_exp_p_minus_2[12] = B200_EXP_P_MINUS_2;
+static const uint32_t h_exp_sqrt[12] = B200_EXP_P_PLUS_1_DIV_4;
+static const uint32_t h_exp_p_minus_3_div_4[12] = B200_EXP_P_MINUS_3_DIV_4;
+static const uint32_t h_exp_p_minus_1_div_2[12] = B200_EXP_P_MINUS_1_DIV_2;
+
+#if defined(__CUDA_ARCH__)
+#define B200_EXP_TABLE(name) d_##name
+#else
+#define B200_EXP_TABLE(name) h_##name
+#endif
+
+// r = a^e, e given as 12 little-endian words; left-to-right binary (a != secret: variable time is fine here).
+B200_HD void fp_pow(Fp& r, const Fp& a, const uint32_t* e) {
+    Fp acc = fp_one();
+    bool started = false;
+#pragma unroll 1
+    for (int w = 11; w >= 0; w--) {
+        const uint32_t word = e[w];
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            if (started) fp_sqr(acc, acc);
+            if ((word >> bit) & 1) {
+                if (started) fp_mul(acc, acc, a); else { acc = a; started = true; }
+            }
+        }
+    }
+    r = acc;
+}
+B200_HD void fp_inv(Fp& r, const Fp& a) { fp_pow(r, a, B200_EXP_TABLE(exp_p_minus_2)); }
+// candidate square root a^((p+1)/4); returns whether it is one
+B200_HD bool fp_sqrt(Fp& r, const Fp& a) {
+    Fp s, c;
+    fp_pow(s, a, B200_EXP_TABLE(exp_sqrt));
+    fp_sqr(c, s);
+    r = s;
+    return fp_eq(c, a);
+}
+
+}  // namespace b200

@@ -1,0 +1,121 @@
+// Fp2 = Fp[u]/(u^2 + 1) for BLS12-381 (G2 coordinates, the twist, line coefficients).
+#pragma once
+#include "fp.cuh"
+
+namespace b200 {
+
+struct Fp2 {
+    Fp c0, c1;
+};
+
+B200_HD Fp2 fp2_zero() { Fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
+B200_HD Fp2 fp2_one() { Fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
+B200_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+B200_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+B200_HD void fp2_add(Fp2& r, const Fp2& a, const Fp2& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+B200_HD void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+B200_HD void fp2_neg(Fp2& r, const Fp2& a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+B200_HD void fp2_dbl(Fp2& r, const Fp2& a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
+B200_HD void fp2_conj(Fp2& r, const Fp2& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
+
+// Karatsuba: 3 Fp products
+#if defined(B200_FP2_NOINLINE)
+B200_HD_NOINLINE
+#else
+B200_HD
+#endif
+void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+    Fp t0, t1, s0, s1, m;
+    fp_mul(t0, a.c0, b.c0);
+    fp_mul(t1, a.c1, b.c1);
+    fp_add(s0, a.c0, a.c1);
+    fp_add(s1, b.c0, b.c1);
+    fp_mul(m, s0, s1);
+    fp_sub(m, m, t0);
+    fp_sub(m, m, t1);
+    fp_sub(r.c0, t0, t1);
+    r.c1 = m;
+}
+// complex squaring: 2 Fp products
+#if defined(B200_FP2_NOINLINE)
+B200_HD_NOINLINE
+#else
+B200_HD
+#endif
+void fp2_sqr(Fp2& r, const Fp2& a) {
+    Fp s, d, m;
+    fp_add(s, a.c0, a.c1);
+    fp_sub(d, a.c0, a.c1);
+    fp_mul(m, a.c0, a.c1);
+    fp_mul(r.c0, s, d);
+    fp_dbl(r.c1, m);
+}
+B200_HD void fp2_mul_fp(Fp2& r, const Fp2& a, const Fp& k) { fp_mul(r.c0, a.c0, k); fp_mul(r.c1, a.c1, k); }
+// multiply by xi = 1 + u
+B200_HD void fp2_mul_xi(Fp2& r, const Fp2& a) {
+    Fp t0, t1;
+    fp_sub(t0, a.c0, a.c1);
+    fp_add(t1, a.c0, a.c1);
+    r.c0 = t0; r.c1 = t1;
+}
+B200_HD void fp2_inv(Fp2& r, const Fp2& a) {
+    Fp n, t;
+    fp_sqr(n, a.c0);
+    fp_sqr(t, a.c1);
+    fp_add(n, n, t);
+    fp_inv(n, n);
+    fp_mul(r.c0, a.c0, n);
+    fp_mul(t, a.c1, n);
+    fp_neg(r.c1, t);
+}
+B200_HD void fp2_pow(Fp2& r, const Fp2& a, const uint32_t* e) {
+    Fp2 acc = fp2_one();
+    bool started = false;
+#pragma unroll 1
+    for (int w = 11; w >= 0; w--) {
+        const uint32_t word = e[w];
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            if (started) fp2_sqr(acc, acc);
+            if ((word >> bit) & 1) {
+                if (started) fp2_mul(acc, acc, a); else { acc = a; started = true; }
+            }
+        }
+    }
+    r = acc;
+}
+// Square root for p = 3 (mod 4) (Adj & Rodriguez-Henriquez, Alg. 9); returns false if `a` is a non-residue.
+B200_HD bool fp2_sqrt(Fp2& r, const Fp2& a) {
+    if (fp2_is_zero(a)) { r = a; return true; }
+    Fp2 a1, alpha, x0, x, chk;
+    fp2_pow(a1, a, B200_EXP_TABLE(exp_p_minus_3_div_4));
+    fp2_sqr(alpha, a1);
+    fp2_mul(alpha, alpha, a);
+    fp2_mul(x0, a1, a);
+    Fp2 minus_one;
+    fp_neg(minus_one.c0, fp_one());
+    minus_one.c1 = fp_zero();
+    if (fp2_eq(alpha, minus_one)) {
+        fp_neg(x.c0, x0.c1);  // u * x0
+        x.c1 = x0.c0;
+    } else {
+        Fp2 b, one = fp2_one();
+        fp2_add(b, one, alpha);
+        fp2_pow(b, b, B200_EXP_TABLE(exp_p_minus_1_div_2));
+        fp2_mul(x, b, x0);
+    }
+    fp2_sqr(chk, x);
+    r = x;
+    return fp2_eq(chk, a);
+}
+// RFC 9380 sgn0 (m = 2)
+B200_HD uint32_t fp2_sgn0(const Fp2& a) {
+    uint32_t s0 = fp_parity(a.c0), z0 = fp_is_zero(a.c0) ? 1u : 0u, s1 = fp_parity(a.c1);
+    return s0 | (z0 & s1);
+}
+// ZCash "lexicographically largest" for Fp2: compare c1 first, then c0
+B200_HD bool fp2_is_lex_largest(const Fp2& a) {
+    return fp_is_zero(a.c1) ? fp_is_lex_largest(a.c0) : fp_is_lex_largest(a.c1);
+}
+
+}  // namespace b200

@@ -1,0 +1,160 @@
+// TEST INFRASTRUCTURE: compiles the product's __host__ __device__ BLS math (ethereum_consensus_b200/csrc/*.cuh)
+// for the CPU so that every layer above the PTX-free Fp arithmetic can be diffed against the big-int oracle
+// without a GPU.  Nothing here is linked into libb200_consensus.so; the product path launches kernels only.
+#include <cstdint>
+#include <cstring>
+
+#include "../../ethereum_consensus_b200/csrc/h2c.cuh"
+#include "../../ethereum_consensus_b200/csrc/pairing.cuh"
+
+using namespace b200;
+#define HM __attribute__((visibility("default")))
+
+static void fp_in(Fp& r, const uint8_t* be48) { Fp raw; fp_from_be_bytes_raw(raw, be48); fp_to_mont(r, raw); }
+static void fp_out(uint8_t* be48, const Fp& a) { Fp raw; fp_from_mont(raw, a); fp_to_be_bytes_raw(be48, raw); }
+static void fp2_in(Fp2& r, const uint8_t* b) { fp_in(r.c0, b); fp_in(r.c1, b + 48); }
+static void fp2_out(uint8_t* b, const Fp2& a) { fp_out(b, a.c0); fp_out(b + 48, a.c1); }
+static void g1_in(G1Aff& p, const uint8_t* b, int inf) { p.inf = inf; fp_in(p.x, b); fp_in(p.y, b + 48); }
+static void g2_in(G2Aff& p, const uint8_t* b, int inf) { p.inf = inf; fp2_in(p.x, b); fp2_in(p.y, b + 96); }
+static void g2_out(uint8_t* b, const G2Aff& p) { fp2_out(b, p.x); fp2_out(b + 96, p.y); }
+
+extern "C" {
+
+// op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqrt(a) (returns ok), 5 neg(a)
+HM int hm_fp_op(int op, const uint8_t* a48, const uint8_t* b48, uint8_t* out48) {
+    Fp a, b, r;
+    fp_in(a, a48); fp_in(b, b48);
+    int ok = 1;
+    switch (op) {
+    case 0: fp_add(r, a, b); break;
+    case 1: fp_sub(r, a, b); break;
+    case 2: fp_mul(r, a, b); break;
+    case 3: fp_inv(r, a); break;
+    case 4: ok = fp_sqrt(r, a); break;
+    default: fp_neg(r, a); break;
+    }
+    fp_out(out48, r);
+    return ok;
+}
+// op: 0 mul, 1 sqr(a), 2 inv(a), 3 sqrt(a) (returns ok), 4 sgn0(a) (returned), 5 lex_largest(a) (returned)
+HM int hm_fp2_op(int op, const uint8_t* a96, const uint8_t* b96, uint8_t* out96) {
+    Fp2 a, b, r = fp2_zero();
+    fp2_in(a, a96); fp2_in(b, b96);
+    int ret = 1;
+    switch (op) {
+    case 0: fp2_mul(r, a, b); break;
+    case 1: fp2_sqr(r, a); break;
+    case 2: fp2_inv(r, a); break;
+    case 3: ret = fp2_sqrt(r, a); break;
+    case 4: ret = int(fp2_sgn0(a)); break;
+    default: ret = fp2_is_lex_largest(a); break;
+    }
+    fp2_out(out96, r);
+    return ret;
+}
+HM int hm_g1_key_validate(const uint8_t* in48, uint8_t* out_xy96, uint8_t* recompressed48) {
+    G1Aff p;
+    int rc = g1_key_validate(p, in48);
+    if (rc == 0) { fp_out(out_xy96, p.x); fp_out(out_xy96 + 48, p.y); g1_compress(recompressed48, p); }
+    return rc;
+}
+HM int hm_g1_uncompress(const uint8_t* in48, uint8_t* out_xy96, int* inf) {
+    G1Aff p;
+    int rc = g1_uncompress(p, in48);
+    if (rc == 0) { fp_out(out_xy96, p.x); fp_out(out_xy96 + 48, p.y); *inf = int(p.inf); }
+    return rc;
+}
+HM int hm_g2_uncompress(const uint8_t* in96, uint8_t* out192, int* inf, int* in_group, uint8_t* recompressed96) {
+    G2Aff p;
+    int rc = g2_uncompress(p, in96);
+    if (rc == 0) { g2_out(out192, p); *inf = int(p.inf); *in_group = g2_in_subgroup(p); g2_compress(recompressed96, p); }
+    return rc;
+}
+HM void hm_hash_to_field(const uint8_t* msg, size_t len, uint8_t* out192) {
+    Fp2 u0, u1;
+    hash_to_field_fp2(u0, u1, msg, len);
+    fp2_out(out192, u0); fp2_out(out192 + 96, u1);
+}
+HM void hm_sswu_iso(const uint8_t* t96, uint8_t* out192, int* inf) {
+    Fp2 t, x, y;
+    fp2_in(t, t96);
+    sswu_map(x, y, t);
+    G2Jac j;
+    iso3_map(j, x, y);
+    G2Aff a;
+    jac_to_aff(a, j);
+    g2_out(out192, a);
+    *inf = int(a.inf);
+}
+HM void hm_hash_to_g2(const uint8_t* msg, size_t len, uint8_t* out192, int* inf) {
+    G2Aff h;
+    hash_to_g2(h, msg, len);
+    g2_out(out192, h);
+    *inf = int(h.inf);
+}
+// prod e(P_i, Q_i) == 1 ?   g1: n x 96 bytes (x,y), g2: n x 192 bytes, inf flags per point (bit0 g1, bit1 g2)
+HM int hm_pairing_check(int n, const uint8_t* g1, const uint8_t* g2, const uint8_t* inf) {
+    Fp12 acc = fp12_one(), f;
+    for (int i = 0; i < n; i++) {
+        G1Aff p; G2Aff q;
+        g1_in(p, g1 + 96 * i, inf[i] & 1);
+        g2_in(q, g2 + 192 * i, (inf[i] >> 1) & 1);
+        miller_loop(f, p, q);
+        fp12_mul(acc, acc, f);
+    }
+    return final_exp_is_one(acc);
+}
+// fp12 self-consistency: returns bitmask of passed checks (inverse, frobenius^12... ) on a = miller_loop(g1, g2 gens)
+HM int hm_fp12_selftest(void) {
+    G1Aff p; p.inf = 0; { const Fp x = B200_FP_G1_X, y = B200_FP_G1_Y; p.x = x; p.y = y; }
+    G2Aff q;
+    uint8_t msg[3] = {1, 2, 3};
+    hash_to_g2(q, msg, 3);
+    Fp12 a, b, c;
+    miller_loop(a, p, q);
+    int ok = 0;
+    fp12_inv(b, a); fp12_mul(c, a, b); if (fp12_is_one(c)) ok |= 1;
+    fp12_sqr(b, a); fp12_mul(c, a, a);
+    bool same = fp2_eq(b.c0.c0, c.c0.c0) && fp2_eq(b.c1.c2, c.c1.c2) && fp2_eq(b.c0.c1, c.c0.c1) && fp2_eq(b.c1.c0, c.c1.c0) &&
+                fp2_eq(b.c0.c2, c.c0.c2) && fp2_eq(b.c1.c1, c.c1.c1);
+    if (same) ok |= 2;
+    // frobenius^1 applied 12 times is the identity; frobenius<2> == frobenius<1> twice; <3> == thrice
+    b = a;
+    for (int i = 0; i < 12; i++) { fp12_frobenius<1>(c, b); b = c; }
+    fp12_inv(c, a); fp12_mul(c, c, b); if (fp12_is_one(c)) ok |= 4;
+    fp12_frobenius<1>(b, a); fp12_frobenius<1>(c, b); fp12_frobenius<2>(b, a);
+    { Fp12 d; fp12_inv(d, c); fp12_mul(d, d, b); if (fp12_is_one(d)) ok |= 8; }
+    fp12_frobenius<1>(b, c); fp12_frobenius<3>(c, a);
+    { Fp12 d; fp12_inv(d, c); fp12_mul(d, d, b); if (fp12_is_one(d)) ok |= 16; }
+    return ok;
+}
+
+// the reference wrapper's fast_aggregate_verify (crypto/bls.rs:114-132), sequentially, from the HD pieces
+HM int hm_fast_aggregate_verify(const uint8_t* pks, size_t k, const uint8_t* msg, size_t len, const uint8_t* sig) {
+    G1Jac acc;
+    jac_set_inf(acc);
+    for (size_t i = 0; i < k; i++) {
+        G1Aff p;
+        int rc = g1_key_validate(p, pks + 48 * i);
+        if (rc) return rc;
+        jac_add_mixed(acc, acc, p.x, p.y);
+    }
+    G2Aff s;
+    int rc = g2_uncompress(s, sig);
+    if (rc) return rc;
+    if (k == 0) return BLS_VERIFY_FAIL;
+    if (!g2_in_subgroup(s)) return BLS_VERIFY_FAIL;
+    G1Aff agg;
+    jac_to_aff(agg, acc);
+    if (agg.inf) return BLS_VERIFY_FAIL;
+    G2Aff h;
+    hash_to_g2(h, msg, len);
+    G1Aff ng; ng.inf = 0; { const Fp x = B200_FP_G1_X, y = B200_FP_G1_NEG_Y; ng.x = x; ng.y = y; }
+    Fp12 f1, f2;
+    miller_loop(f1, agg, h);
+    miller_loop(f2, ng, s);
+    fp12_mul(f1, f1, f2);
+    return final_exp_is_one(f1) ? BLS_SUCCESS : BLS_VERIFY_FAIL;
+}
+
+}  // extern "C"
