@@ -1,0 +1,143 @@
+// G1 side of the BLS pipeline: per-public-key validation (the dominant cost of the reference's
+// fast_aggregate_verify, /root/reference/ethereum-consensus/src/crypto/bls.rs:119-123 -> :283) and the per-tuple
+// aggregation blst performs in `AggregatePublicKey::aggregate`.
+//
+// k_g1_validate : one thread per key, Fp limbs in registers; 48 B in, 100 B out.  Integer-pipe bound.
+// k_g1_aggregate: one warp per tuple; lanes stride over the tuple's keys with mixed additions, then a
+//                 5-round shared-memory tree of Jacobian additions; lane 0 normalises to affine.
+#include <cuda_runtime.h>
+
+#include "bls_kernels.cuh"
+
+namespace b200 {
+namespace {
+
+__global__ void __launch_bounds__(128) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
+                                                      G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[48];
+    const uint4* src = reinterpret_cast<const uint4*>(keys + size_t(i) * 48);
+    uint4* dst = reinterpret_cast<uint4*>(b);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    G1Aff p;
+    const int32_t rc = g1_key_validate(p, b);
+    codes[i] = rc;
+    if (rc == BLS_SUCCESS) out[i] = p;
+}
+
+constexpr int kAggWarps = 4;
+
+__global__ void __launch_bounds__(32 * kAggWarps) k_g1_aggregate(const G1Aff* __restrict__ keys,
+                                                                  const int32_t* __restrict__ key_codes,
+                                                                  const uint32_t* __restrict__ index,
+                                                                  const uint32_t* __restrict__ off, uint32_t n_tuples,
+                                                                  G1Aff* __restrict__ agg, int32_t* __restrict__ pk_code,
+                                                                  uint32_t* __restrict__ flags, uint32_t extra_flags) {
+    __shared__ G1Jac part[kAggWarps][32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * kAggWarps + warp;
+    if (t >= n_tuples) return;  // whole warp exits together
+    const uint32_t lo = off[t], hi = off[t + 1];
+    // first failing key in order
+    uint32_t first_bad = 0xffffffffu;
+    for (uint32_t k = lo + lane; k < hi; k += 32) {
+        const uint32_t id = index ? index[k] : k;
+        if (key_codes[id] != BLS_SUCCESS) { first_bad = k; break; }
+    }
+    for (int s = 16; s > 0; s >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, s));
+    if (first_bad != 0xffffffffu) {
+        if (lane == 0) {
+            pk_code[t] = key_codes[index ? index[first_bad] : first_bad];
+            flags[t] = 0;
+        }
+        return;
+    }
+    if (agg == nullptr) {  // code scan only
+        if (lane == 0) { pk_code[t] = BLS_SUCCESS; flags[t] = (hi == lo ? TUPLE_FLAG_EMPTY : 0u) | extra_flags; }
+        return;
+    }
+    G1Jac acc;
+    jac_set_inf(acc);
+    for (uint32_t k = lo + lane; k < hi; k += 32) {
+        const G1Aff q = keys[index ? index[k] : k];
+        jac_add_mixed(acc, acc, q.x, q.y);
+    }
+    part[warp][lane] = acc;
+    __syncwarp();
+    for (int s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            G1Jac a = part[warp][lane], b = part[warp][lane + s];
+            jac_add(a, a, b);
+            part[warp][lane] = a;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        G1Aff a;
+        jac_to_aff(a, part[warp][0]);
+        agg[t] = a;
+        pk_code[t] = BLS_SUCCESS;
+        flags[t] = (hi == lo ? TUPLE_FLAG_EMPTY : 0u) | (a.inf ? TUPLE_FLAG_AGG_INF : 0u) | extra_flags;
+    }
+}
+
+__global__ void k_g1_compress(const G1Aff* p, uint8_t* out48) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) g1_compress(out48, *p);
+}
+__global__ void k_neg_g1(G1Aff* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        G1Aff g;
+        const Fp x = B200_FP_G1_X, y = B200_FP_G1_NEG_Y;
+        g.x = x; g.y = y; g.inf = 0;
+        *out = g;
+    }
+}
+
+// Fp self-test: random a, b; checks (a*b)*c == a*(b*c), a*(b+c) == a*b + a*c, a * a^-1 == 1 for a few values
+__global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = (uint64_t(seed) << 32) | i;
+    auto next = [&]() { s += 0x9e3779b97f4a7c15ull; uint64_t z = s; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+                        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return uint32_t((z ^ (z >> 31)) >> 16); };
+    Fp a, b, c;
+    for (int k = 0; k < 12; k++) { a.l[k] = next(); b.l[k] = next(); c.l[k] = next(); }
+    a.l[11] &= 0x0fffffffu; b.l[11] &= 0x0fffffffu; c.l[11] &= 0x0fffffffu;  // < p
+    Fp ab, bc, l, r, t;
+    uint32_t bad = 0;
+    fp_mul(ab, a, b); fp_mul(l, ab, c); fp_mul(bc, b, c); fp_mul(r, a, bc);
+    if (!fp_eq(l, r)) bad++;
+    fp_add(t, b, c); fp_mul(l, a, t); fp_mul(r, a, c); fp_add(r, r, ab);
+    if (!fp_eq(l, r)) bad++;
+    fp_sqr(l, a); fp_mul(r, a, a);
+    if (!fp_eq(l, r)) bad++;
+    if ((i & 63) == 0 && !fp_is_zero(a)) {
+        fp_inv(t, a); fp_mul(t, t, a);
+        if (!fp_eq(t, fp_one())) bad++;
+    }
+    if (bad) atomicAdd(out_mismatch, bad);
+}
+
+}  // namespace
+
+void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
+    if (!n) return;
+    k_g1_validate<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(keys, n, out, codes);
+}
+void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,
+                         uint32_t n_tuples, G1Aff* agg, int32_t* pk_code, uint32_t* flags, uint32_t extra_flags,
+                         void* stream) {
+    if (!n_tuples) return;
+    k_g1_aggregate<<<(n_tuples + kAggWarps - 1) / kAggWarps, 32 * kAggWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+        keys, key_codes, index, off, n_tuples, agg, pk_code, flags, extra_flags);
+}
+void launch_g1_compress(const G1Aff* p, uint8_t* out48, void* stream) {
+    k_g1_compress<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p, out48);
+}
+void launch_neg_g1(G1Aff* out, void* stream) { k_neg_g1<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out); }
+void launch_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch, void* stream) {
+    k_fp_selftest<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(n, seed, out_mismatch);
+}
+
+}  // namespace b200

@@ -1,0 +1,98 @@
+// G2 side of the BLS pipeline: signature decompression + subgroup check (blst `Signature::from_bytes` and the
+// `sig_groupcheck = true` of /root/reference/ethereum-consensus/src/crypto/bls.rs:71,106,126) and hash_to_G2 of
+// the signing roots.  One thread per signature / message; these kernels see only T (thousands) of items, so
+// they run concurrently with the wide G1 kernels on a second stream.
+#define B200_FP_MUL_NOINLINE 1
+#define B200_FP2_NOINLINE 1
+#define B200_TOWER_NOINLINE 1
+#include <cuda_runtime.h>
+
+#include "bls_kernels.cuh"
+#include "h2c.cuh"
+
+namespace b200 {
+namespace {
+
+__global__ void __launch_bounds__(64) k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
+                                                       int32_t* __restrict__ sig_code) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[96];
+    const uint4* src = reinterpret_cast<const uint4*>(sigs + size_t(i) * 96);
+    uint4* dst = reinterpret_cast<uint4*>(b);
+#pragma unroll
+    for (int k = 0; k < 6; k++) dst[k] = src[k];
+    G2Aff q;
+    int32_t rc = g2_uncompress(q, b);
+    if (rc == BLS_SUCCESS) {
+        out[i] = q;
+        if (!g2_in_subgroup(q)) rc = SIG_NOT_IN_GROUP;
+    }
+    sig_code[i] = rc;
+}
+
+__global__ void __launch_bounds__(64) k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ moff,
+                                                    uint32_t n, G2Aff* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G2Aff h;
+    hash_to_g2(h, msgs + moff[i], size_t(moff[i + 1] - moff[i]));
+    out[i] = h;
+}
+
+// `aggregate` (crypto/bls.rs:79-93): every signature decoded already; group-check each (first failure in order
+// wins), sum, compress.  One warp: lanes stride, shared-memory tree.
+__global__ void __launch_bounds__(32) k_g2_sum_compress(const G2Aff* __restrict__ sigs, const int32_t* __restrict__ sig_code,
+                                                         uint32_t n, uint8_t* out96, int32_t* out_code) {
+    __shared__ G2Jac part[32];
+    const uint32_t lane = threadIdx.x;
+    uint32_t first_bad = 0xffffffffu;
+    for (uint32_t k = lane; k < n; k += 32)
+        if (sig_code[k] != SIG_OK) { first_bad = k; break; }
+    for (int s = 16; s > 0; s >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, s));
+    // decode errors take precedence over group-check errors (all signatures are decoded before any is checked)
+    uint32_t first_dec = 0xffffffffu;
+    for (uint32_t k = lane; k < n; k += 32)
+        if (sig_code[k] > 0) { first_dec = k; break; }
+    for (int s = 16; s > 0; s >>= 1) first_dec = min(first_dec, __shfl_xor_sync(0xffffffffu, first_dec, s));
+    if (first_dec != 0xffffffffu) { if (lane == 0) *out_code = sig_code[first_dec]; return; }
+    if (first_bad != 0xffffffffu) { if (lane == 0) *out_code = BLS_POINT_NOT_IN_GROUP; return; }
+    G2Jac acc;
+    jac_set_inf(acc);
+    for (uint32_t k = lane; k < n; k += 32) {
+        const G2Aff q = sigs[k];
+        if (!q.inf) jac_add_mixed(acc, acc, q.x, q.y);
+    }
+    part[lane] = acc;
+    __syncwarp();
+    for (int s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            G2Jac a = part[lane], b = part[lane + s];
+            jac_add(a, a, b);
+            part[lane] = a;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        G2Aff a;
+        jac_to_aff(a, part[0]);
+        g2_compress(out96, a);
+        *out_code = BLS_SUCCESS;
+    }
+}
+
+}  // namespace
+
+void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream) {
+    if (!n) return;
+    k_g2_sig_decode<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
+}
+void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* stream) {
+    if (!n) return;
+    k_hash_to_g2<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, out);
+}
+void launch_g2_sum_compress(const G2Aff* sigs, const int32_t* sig_code, uint32_t n, uint8_t* out96, int32_t* out_code, void* stream) {
+    k_g2_sum_compress<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sigs, sig_code, n, out96, out_code);
+}
+
+}  // namespace b200

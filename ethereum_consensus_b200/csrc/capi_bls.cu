@@ -1,0 +1,444 @@
+// extern "C" entry points — the BLS half of include/b200_consensus.h — and the host orchestration of the batch
+// pipeline.  Every function below is a drop-in for one body in
+// /root/reference/ethereum-consensus/src/crypto/bls.rs (line ranges in the header); all curve arithmetic runs in
+// the kernels of bls_g1.cu / bls_g2.cu / bls_pairing.cu.  The host only stages bytes and index arrays.
+//
+// Flow for T tuples with NK public keys in total (strict mode):
+//   stream A: H2D keys,offsets | K1 key_validate (NK threads) | K2 per-tuple aggregate (T warps) ----+
+//   stream B: H2D sigs,msgs    | K3 sig decompress+subgroup (T) | K4 hash_to_G2 (T) ---------------+ |
+//   stream A: wait(B) | K5 Miller loops (2T threads) | K6 Gt product + final exponentiation (T) | D2H codes
+// Registry mode skips K1: validated affine keys stay resident in HBM and K2 gathers them by validator index.
+#include <cstring>
+#include <vector>
+
+#include "bls_kernels.cuh"
+#include "engine.h"
+
+namespace b200 {
+
+struct BlsState {
+    cudaStream_t sb = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    DevBuf keys, key_aff, key_code, g1pts, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out;
+    PinnedBuf stage;
+    G1Aff* d_negg1 = nullptr;
+    // registry (validated keys resident on the device)
+    DevBuf reg_aff, reg_code;
+    size_t reg_n = 0;
+    float last_dominant_ms = 0.f;
+};
+
+static int32_t bls_state(Engine& e, BlsState** out) {
+    if (!e.bls) {
+        BlsState* s = new BlsState();
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&s->sb, cudaStreamNonBlocking));
+        B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
+        B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
+        B200_CUDA_TRY(cudaEventCreate(&s->ev_k0));
+        B200_CUDA_TRY(cudaEventCreate(&s->ev_k1));
+        B200_CUDA_TRY(cudaEventCreate(&s->ev_d0));
+        B200_CUDA_TRY(cudaEventCreate(&s->ev_d1));
+        B200_CUDA_TRY(cudaMalloc(&s->d_negg1, sizeof(G1Aff)));
+        launch_neg_g1(s->d_negg1, e.stream);
+        e.launches++;
+        B200_CUDA_TRY(cudaGetLastError());
+        B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+        e.bls = s;
+    }
+    *out = static_cast<BlsState*>(e.bls);
+    return B200_SUCCESS;
+}
+
+struct Guard {
+    std::unique_lock<std::mutex> lk;
+    explicit Guard(Engine& e) : lk(e.mu) {}
+};
+static int32_t check_ready(Engine& e) {
+    if (!e.ready) { e.last_error = "b200_init has not been called (or failed)"; return B200_ERR_NOT_INITIALIZED; }
+    cudaError_t ce = cudaSetDevice(e.device);
+    if (ce != cudaSuccess) { e.last_error = cudaGetErrorString(ce); return B200_ERR_CUDA; }
+    return B200_SUCCESS;
+}
+
+enum PairMode { MODE_FAST_AGGREGATE = 0, MODE_AGGREGATE = 1 };
+
+// Core: `n_tuples` tuples.  MODE_FAST_AGGREGATE: tuple t sums keys [key_off[t], key_off[t+1]) and checks
+// e(sum, H(msg_t)) e(-g1, sig_t) == 1.  MODE_AGGREGATE: one tuple, pairs (key_i, H(msg_i)) + (-g1, sig).
+// keys: host bytes (strict) or nullptr with `index` (registry gather).  msgs: host bytes + offsets (n_msgs + 1).
+static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* keys, uint32_t n_keys,
+                          const uint32_t* index, uint32_t n_index, const uint32_t* key_off, const uint8_t* msgs,
+                          const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
+                          bool force_fail_shape, int32_t* out_codes) {
+    const bool registry = (keys == nullptr && index != nullptr);
+    const uint32_t T = n_tuples;
+    const uint32_t n_g1 = (mode == MODE_FAST_AGGREGATE ? T : n_keys) + 1;  // + (-g1)
+    const uint32_t n_pairs = (mode == MODE_FAST_AGGREGATE) ? 2 * T : (force_fail_shape ? 0 : n_msgs + 1);
+    const uint32_t n_g2 = n_msgs + T;
+    const uint32_t msg_bytes = msg_off[n_msgs];
+
+    // ---- device buffers
+    B200_CUDA_TRY(s.keys.reserve(size_t(n_keys) * 48 + 64));
+    B200_CUDA_TRY(s.key_aff.reserve(size_t(n_keys + 1) * sizeof(G1Aff)));
+    B200_CUDA_TRY(s.key_code.reserve(size_t(n_keys + 1) * 4));
+    B200_CUDA_TRY(s.g1pts.reserve(size_t(n_g1) * sizeof(G1Aff)));
+    B200_CUDA_TRY(s.pk_code.reserve(size_t(T + 1) * 4));
+    B200_CUDA_TRY(s.flags.reserve(size_t(T + 1) * 4));
+    B200_CUDA_TRY(s.sigs.reserve(size_t(T) * 96 + 64));
+    B200_CUDA_TRY(s.g2pts.reserve(size_t(n_g2 + 1) * sizeof(G2Aff)));
+    B200_CUDA_TRY(s.sig_code.reserve(size_t(T + 1) * 4));
+    B200_CUDA_TRY(s.msgs.reserve(size_t(msg_bytes) + 64));
+    B200_CUDA_TRY(s.f.reserve(size_t(n_pairs + 1) * sizeof(Fp12)));
+    B200_CUDA_TRY(s.out.reserve(size_t(T + 1) * 4));
+
+    // ---- small host-built arrays, one staged copy: [key_off | index | msg_off | g1_idx | g2_idx | pair_tuple | pair_off]
+    const uint32_t n_koff = (mode == MODE_FAST_AGGREGATE) ? T + 1 : 2;
+    std::vector<uint32_t> small;
+    small.reserve(size_t(n_koff) + n_index + n_msgs + 1 + 3 * size_t(n_pairs) + T + 1 + 8);
+    const size_t o_koff = small.size();
+    if (mode == MODE_FAST_AGGREGATE) small.insert(small.end(), key_off, key_off + T + 1);
+    else { small.push_back(0); small.push_back(n_keys); }
+    const size_t o_index = small.size();
+    if (registry) small.insert(small.end(), index, index + n_index);
+    const size_t o_moff = small.size();
+    small.insert(small.end(), msg_off, msg_off + n_msgs + 1);
+    const size_t o_g1i = small.size();
+    small.resize(small.size() + 3 * size_t(n_pairs) + T + 1);
+    uint32_t* g1i = small.data() + o_g1i;
+    uint32_t* g2i = g1i + n_pairs;
+    uint32_t* ptu = g2i + n_pairs;
+    uint32_t* poff = ptu + n_pairs;
+    if (mode == MODE_FAST_AGGREGATE) {
+        for (uint32_t t = 0; t < T; t++) {
+            g1i[2 * t] = t;          g2i[2 * t] = t;          // (agg_t, H(msg_t))
+            g1i[2 * t + 1] = T;      g2i[2 * t + 1] = n_msgs + t;  // (-g1, sig_t)
+            ptu[2 * t] = ptu[2 * t + 1] = t;
+            poff[t] = 2 * t;
+        }
+        poff[T] = 2 * T;
+    } else {
+        for (uint32_t i = 0; i + 1 < n_pairs; i++) { g1i[i] = i; g2i[i] = i; ptu[i] = 0; }
+        if (n_pairs) { g1i[n_pairs - 1] = n_keys; g2i[n_pairs - 1] = n_msgs; ptu[n_pairs - 1] = 0; }
+        poff[0] = 0; poff[1] = n_pairs;
+    }
+    const size_t small_bytes = small.size() * 4;
+    B200_CUDA_TRY(s.stage.reserve(small_bytes + size_t(T + 1) * 4 + 64));
+    B200_CUDA_TRY(s.small.reserve(small_bytes + 64));
+    memcpy(s.stage.p, small.data(), small_bytes);
+    int32_t* h_out = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(s.stage.p) + ((small_bytes + 15) & ~size_t(15)));
+
+    cudaStream_t sa = e.stream, sb = s.sb;
+    uint32_t* d_small = static_cast<uint32_t*>(s.small.p);
+    G1Aff* d_g1 = static_cast<G1Aff*>(s.g1pts.p);
+    G2Aff* d_g2 = static_cast<G2Aff*>(s.g2pts.p);
+    const G1Aff* key_aff = registry ? static_cast<const G1Aff*>(s.reg_aff.p) : static_cast<const G1Aff*>(s.key_aff.p);
+    const int32_t* key_code = registry ? static_cast<const int32_t*>(s.reg_code.p) : static_cast<const int32_t*>(s.key_code.p);
+
+    // ---- stream B: signatures + messages
+    B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
+    B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));  // orders after any previous call's use of the buffers
+    if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
+    if (msg_bytes) B200_CUDA_TRY(cudaMemcpyAsync(s.msgs.p, msgs, msg_bytes, cudaMemcpyHostToDevice, sb));
+    // ---- stream A: small arrays, keys
+    B200_CUDA_TRY(cudaMemcpyAsync(d_small, s.stage.p, small_bytes, cudaMemcpyHostToDevice, sa));
+    if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
+    B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
+    B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));  // msg_off lives in d_small
+    B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
+    launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), sb);
+    launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, sb);
+    e.launches += (T ? 1 : 0) + (n_msgs ? 1 : 0);
+    B200_CUDA_TRY(cudaEventRecord(s.ev_b, sb));
+
+    // ---- stream A: public keys
+    B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
+    if (!registry && n_keys) {
+        launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, static_cast<G1Aff*>(s.key_aff.p),
+                           static_cast<int32_t*>(s.key_code.p), sa);
+        e.launches++;
+    }
+    B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
+    const uint32_t n_agg_tuples = (mode == MODE_FAST_AGGREGATE) ? T : 1;
+    launch_g1_aggregate(key_aff, key_code, registry ? d_small + o_index : nullptr, d_small + o_koff, n_agg_tuples,
+                        mode == MODE_FAST_AGGREGATE ? d_g1 : nullptr, static_cast<int32_t*>(s.pk_code.p),
+                        static_cast<uint32_t*>(s.flags.p), force_fail_shape ? uint32_t(TUPLE_FLAG_EMPTY) : 0u, sa);
+    e.launches++;
+    const G1Aff* pair_g1 = d_g1;
+    if (mode == MODE_FAST_AGGREGATE) {
+        B200_CUDA_TRY(cudaMemcpyAsync(d_g1 + T, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
+    } else {
+        G1Aff* ka = static_cast<G1Aff*>(s.key_aff.p);
+        B200_CUDA_TRY(cudaMemcpyAsync(ka + n_keys, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
+        pair_g1 = ka;  // len(msgs) != len(pks) or no keys: flagged EMPTY above -> VERIFY_FAIL after the decoding checks
+    }
+    // ---- join, pairing
+    B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_b, 0));
+    launch_miller(pair_g1, d_small + o_g1i, d_g2, d_small + o_g1i + n_pairs, d_small + o_g1i + 2 * size_t(n_pairs),
+                  static_cast<const int32_t*>(s.pk_code.p), static_cast<const uint32_t*>(s.flags.p),
+                  static_cast<const int32_t*>(s.sig_code.p), n_pairs, static_cast<Fp12*>(s.f.p), sa);
+    launch_final(static_cast<const Fp12*>(s.f.p), d_small + o_g1i + 3 * size_t(n_pairs), static_cast<const int32_t*>(s.pk_code.p),
+                 static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), T,
+                 static_cast<int32_t*>(s.out.p), sa);
+    e.launches += (n_pairs ? 1 : 0) + (T ? 1 : 0);
+    B200_CUDA_TRY(cudaEventRecord(s.ev_k1, sa));
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(h_out + 4, s.out.p, size_t(T) * 4, cudaMemcpyDeviceToHost, sa));
+    B200_CUDA_TRY(cudaStreamSynchronize(sa));
+    B200_CUDA_TRY(cudaStreamSynchronize(sb));
+    B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, s.ev_k0, s.ev_k1));
+    B200_CUDA_TRY(cudaEventElapsedTime(&s.last_dominant_ms, s.ev_d0, s.ev_d1));
+    for (uint32_t t = 0; t < T; t++) out_codes[t] = h_out[4 + t];
+    return B200_SUCCESS;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+float b200_last_dominant_kernel_ms(void) {
+    Engine& e = engine();
+    return e.bls ? static_cast<BlsState*>(e.bls)->last_dominant_ms : 0.f;
+}
+
+int32_t b200_fp_selftest(uint32_t n, uint32_t seed, uint32_t* mismatches) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!mismatches) return B200_ERR_BAD_ARG;
+    uint32_t* d = nullptr;
+    B200_CUDA_TRY(cudaMalloc(&d, 4));
+    B200_CUDA_TRY(cudaMemsetAsync(d, 0, 4, e.stream));
+    launch_fp_selftest(n, seed, d, e.stream);
+    e.launches++;
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(mismatches, d, 4, cudaMemcpyDeviceToHost, e.stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    cudaFree(d);
+    return B200_SUCCESS;
+}
+
+int32_t b200_fast_aggregate_verify_batch(const uint8_t* pks_flat, const uint32_t* pk_offsets, const uint8_t* msgs32,
+                                         const uint8_t* sigs, size_t n_tuples, int32_t* out_codes) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (n_tuples == 0) return B200_SUCCESS;
+    if (!pk_offsets || !msgs32 || !sigs || !out_codes || n_tuples > 0x3fffffffu) return B200_ERR_BAD_ARG;
+    for (size_t t = 0; t < n_tuples; t++)
+        if (pk_offsets[t] > pk_offsets[t + 1]) return B200_ERR_BAD_ARG;
+    const uint32_t nk = pk_offsets[n_tuples];
+    if (nk && !pks_flat) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    std::vector<uint32_t> moff(n_tuples + 1);
+    for (size_t t = 0; t <= n_tuples; t++) moff[t] = uint32_t(32 * t);
+    return run_verify(e, *s, MODE_FAST_AGGREGATE, pks_flat, nk, nullptr, 0, pk_offsets, msgs32, moff.data(),
+                      uint32_t(n_tuples), sigs, uint32_t(n_tuples), false, out_codes);
+}
+
+int32_t b200_registry_load(const uint8_t* pks_flat, size_t n) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if ((!pks_flat && n) || n > 0x7fffffffu) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    B200_CUDA_TRY(s->keys.reserve(n * 48 + 64));
+    B200_CUDA_TRY(s->reg_aff.reserve((n + 1) * sizeof(G1Aff)));
+    B200_CUDA_TRY(s->reg_code.reserve((n + 1) * 4));
+    if (n) B200_CUDA_TRY(cudaMemcpyAsync(s->keys.p, pks_flat, n * 48, cudaMemcpyHostToDevice, e.stream));
+    B200_CUDA_TRY(cudaEventRecord(s->ev_k0, e.stream));
+    launch_g1_validate(static_cast<const uint8_t*>(s->keys.p), uint32_t(n), static_cast<G1Aff*>(s->reg_aff.p),
+                       static_cast<int32_t*>(s->reg_code.p), e.stream);
+    e.launches += n ? 1 : 0;
+    B200_CUDA_TRY(cudaEventRecord(s->ev_k1, e.stream));
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, s->ev_k0, s->ev_k1));
+    s->last_dominant_ms = e.last_kernel_ms;
+    s->reg_n = n;
+    return B200_SUCCESS;
+}
+
+int32_t b200_registry_key_codes(int32_t* out_codes, size_t n) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    if (!out_codes || n > s->reg_n) return B200_ERR_BAD_ARG;
+    if (n) B200_CUDA_TRY(cudaMemcpy(out_codes, s->reg_code.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200_SUCCESS;
+}
+
+int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indices, const uint32_t* offsets, const uint8_t* msgs32,
+                                                 const uint8_t* sigs, size_t n_tuples, int32_t* out_codes) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (n_tuples == 0) return B200_SUCCESS;
+    if (!offsets || !msgs32 || !sigs || !out_codes || n_tuples > 0x3fffffffu) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    for (size_t t = 0; t < n_tuples; t++)
+        if (offsets[t] > offsets[t + 1]) return B200_ERR_BAD_ARG;
+    const uint32_t ni = offsets[n_tuples];
+    if (ni && !indices) return B200_ERR_BAD_ARG;
+    for (uint32_t i = 0; i < ni; i++)
+        if (indices[i] >= s->reg_n) { e.last_error = "validator index outside the loaded registry"; return B200_ERR_BAD_ARG; }
+    std::vector<uint32_t> moff(n_tuples + 1);
+    for (size_t t = 0; t <= n_tuples; t++) moff[t] = uint32_t(32 * t);
+    static const uint32_t dummy = 0;
+    return run_verify(e, *s, MODE_FAST_AGGREGATE, nullptr, 0, indices ? indices : &dummy, ni, offsets, msgs32, moff.data(),
+                      uint32_t(n_tuples), sigs, uint32_t(n_tuples), false, out_codes);
+}
+
+// crypto/bls.rs:114-132 — `public_keys: &[&PublicKey]` is an array of pointers into the validator registry
+int32_t b200_fast_aggregate_verify(const uint8_t* const* pks, size_t k, const uint8_t* msg, size_t msg_len,
+                                   const uint8_t sig[96]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if ((!pks && k) || (!msg && msg_len) || !sig || k > 0x7fffffffu || msg_len > 0x7fffffffu) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    std::vector<uint8_t> flat(k * 48);
+    for (size_t i = 0; i < k; i++) memcpy(flat.data() + 48 * i, pks[i], 48);
+    const uint32_t koff[2] = {0, uint32_t(k)}, moff[2] = {0, uint32_t(msg_len)};
+    int32_t code = B200_ERR_CUDA;
+    rc = run_verify(e, *s, MODE_FAST_AGGREGATE, flat.data(), uint32_t(k), nullptr, 0, koff, msg, moff, 1, sig, 1, false, &code);
+    return rc ? rc : code;
+}
+
+// crypto/bls.rs:150-160
+int32_t b200_eth_fast_aggregate_verify(const uint8_t* const* pks, size_t k, const uint8_t* msg, size_t msg_len,
+                                       const uint8_t sig[96]) {
+    if (k == 0 && sig) {
+        bool inf = sig[0] == 0xc0;
+        for (int i = 1; i < 96 && inf; i++) inf = sig[i] == 0;
+        if (inf) return B200_SUCCESS;  // G2_POINT_AT_INFINITY with no participants (byte comparison, bls.rs:343-347)
+    }
+    return b200_fast_aggregate_verify(pks, k, msg, msg_len, sig);
+}
+
+// crypto/bls.rs:64-77
+int32_t b200_verify_signature(const uint8_t pk[48], const uint8_t* msg, size_t msg_len, const uint8_t sig[96]) {
+    if (!pk) return B200_ERR_BAD_ARG;
+    const uint8_t* one[1] = {pk};
+    return b200_fast_aggregate_verify(one, 1, msg, msg_len, sig);
+}
+
+// crypto/bls.rs:95-112
+int32_t b200_aggregate_verify(const uint8_t* pks_flat, size_t n_pks, const uint8_t* const* msgs, const size_t* msg_lens,
+                              size_t n_msgs, const uint8_t sig[96]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if ((!pks_flat && n_pks) || ((!msgs || !msg_lens) && n_msgs) || !sig || n_pks > 0x3fffffffu || n_msgs > 0x3fffffffu)
+        return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    const bool shape_fail = (n_pks == 0 || n_pks != n_msgs);
+    std::vector<uint32_t> moff(1, 0);
+    std::vector<uint8_t> flat;
+    if (!shape_fail) {
+        for (size_t i = 0; i < n_msgs; i++) {
+            flat.insert(flat.end(), msgs[i], msgs[i] + msg_lens[i]);
+            moff.push_back(uint32_t(flat.size()));
+        }
+    }
+    int32_t code = B200_ERR_CUDA;
+    rc = run_verify(e, *s, MODE_AGGREGATE, pks_flat, uint32_t(n_pks), nullptr, 0, nullptr, flat.data(), moff.data(),
+                    uint32_t(moff.size() - 1), sig, 1, shape_fail, &code);
+    return rc ? rc : code;
+}
+
+// crypto/bls.rs:79-93
+int32_t b200_aggregate(const uint8_t* sigs_flat, size_t n, uint8_t out[96]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (n == 0) return B200_EMPTY_AGGREGATE;
+    if (!sigs_flat || !out || n > 0x3fffffffu) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    B200_CUDA_TRY(s->sigs.reserve(n * 96 + 64));
+    B200_CUDA_TRY(s->g2pts.reserve((n + 1) * sizeof(G2Aff)));
+    B200_CUDA_TRY(s->sig_code.reserve((n + 1) * 4));
+    B200_CUDA_TRY(s->out.reserve(256));
+    B200_CUDA_TRY(s->stage.reserve(256));
+    cudaStream_t sa = e.stream;
+    B200_CUDA_TRY(cudaMemcpyAsync(s->sigs.p, sigs_flat, n * 96, cudaMemcpyHostToDevice, sa));
+    launch_g2_sig_decode(static_cast<const uint8_t*>(s->sigs.p), uint32_t(n), static_cast<G2Aff*>(s->g2pts.p),
+                         static_cast<int32_t*>(s->sig_code.p), sa);
+    uint8_t* d_out = static_cast<uint8_t*>(s->out.p);
+    launch_g2_sum_compress(static_cast<const G2Aff*>(s->g2pts.p), static_cast<const int32_t*>(s->sig_code.p), uint32_t(n),
+                           d_out + 16, reinterpret_cast<int32_t*>(d_out), sa);
+    e.launches += 2;
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(s->stage.p, d_out, 16 + 96, cudaMemcpyDeviceToHost, sa));
+    B200_CUDA_TRY(cudaStreamSynchronize(sa));
+    const int32_t code = *static_cast<const int32_t*>(s->stage.p);
+    if (code == B200_SUCCESS) memcpy(out, static_cast<const uint8_t*>(s->stage.p) + 16, 96);
+    return code;
+}
+
+// crypto/bls.rs:135-148
+int32_t b200_eth_aggregate_public_keys(const uint8_t* pks_flat, size_t n, uint8_t out[48]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (n == 0) return B200_EMPTY_AGGREGATE;
+    if (!pks_flat || !out || n > 0x3fffffffu) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    B200_CUDA_TRY(s->keys.reserve(n * 48 + 64));
+    B200_CUDA_TRY(s->key_aff.reserve((n + 1) * sizeof(G1Aff)));
+    B200_CUDA_TRY(s->key_code.reserve((n + 1) * 4));
+    B200_CUDA_TRY(s->g1pts.reserve(2 * sizeof(G1Aff)));
+    B200_CUDA_TRY(s->pk_code.reserve(16));
+    B200_CUDA_TRY(s->flags.reserve(16));
+    B200_CUDA_TRY(s->small.reserve(64));
+    B200_CUDA_TRY(s->out.reserve(256));
+    B200_CUDA_TRY(s->stage.reserve(256));
+    cudaStream_t sa = e.stream;
+    uint32_t* h = static_cast<uint32_t*>(s->stage.p);
+    h[0] = 0; h[1] = uint32_t(n);
+    B200_CUDA_TRY(cudaMemcpyAsync(s->small.p, h, 8, cudaMemcpyHostToDevice, sa));
+    B200_CUDA_TRY(cudaMemcpyAsync(s->keys.p, pks_flat, n * 48, cudaMemcpyHostToDevice, sa));
+    launch_g1_validate(static_cast<const uint8_t*>(s->keys.p), uint32_t(n), static_cast<G1Aff*>(s->key_aff.p),
+                       static_cast<int32_t*>(s->key_code.p), sa);
+    launch_g1_aggregate(static_cast<const G1Aff*>(s->key_aff.p), static_cast<const int32_t*>(s->key_code.p), nullptr,
+                        static_cast<const uint32_t*>(s->small.p), 1, static_cast<G1Aff*>(s->g1pts.p),
+                        static_cast<int32_t*>(s->pk_code.p), static_cast<uint32_t*>(s->flags.p), 0u, sa);
+    uint8_t* d_out = static_cast<uint8_t*>(s->out.p);
+    launch_g1_compress(static_cast<const G1Aff*>(s->g1pts.p), d_out, sa);
+    e.launches += 3;
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(h + 4, s->pk_code.p, 4, cudaMemcpyDeviceToHost, sa));
+    B200_CUDA_TRY(cudaMemcpyAsync(h + 8, d_out, 48, cudaMemcpyDeviceToHost, sa));
+    B200_CUDA_TRY(cudaStreamSynchronize(sa));
+    const int32_t code = int32_t(h[4]);
+    if (code == B200_SUCCESS) memcpy(out, h + 8, 48);
+    return code;
+}
+
+}  // extern "C"

@@ -65,7 +65,7 @@ template <class F> B200_HD bool aff_on_curve(const F& x, const F& y) {
 }
 
 // dbl-2009-l (a = 0): 2M + 5S
-template <class F> B200_HD void jac_double(Jac<F>& r, const Jac<F>& p) {
+template <class F> B200_BIG void jac_double(Jac<F>& r, const Jac<F>& p) {
     F A, B, C, D, E, Fq, t;
     f_sqr(A, p.x);
     f_sqr(B, p.y);
@@ -94,7 +94,7 @@ template <class F> B200_HD void jac_double(Jac<F>& r, const Jac<F>& p) {
 
 // r = p + q, q affine and not infinity.  Handles p = inf, p = q (doubling) and p = -q.
 // Optionally returns the pieces the Miller loop needs: Rr = y2*Z^3 - Y and the new Z (= Z*H), see pairing.cuh.
-template <class F> B200_HD void jac_add_mixed(Jac<F>& r, const Jac<F>& p, const F& qx, const F& qy) {
+template <class F> B200_BIG void jac_add_mixed(Jac<F>& r, const Jac<F>& p, const F& qx, const F& qy) {
     if (jac_is_inf(p)) { r.x = qx; r.y = qy; r.z = f_one<F>(); return; }
     F zz, zzz, u2, s2, h, rr;
     f_sqr(zz, p.z);
@@ -126,7 +126,7 @@ template <class F> B200_HD void jac_add_mixed(Jac<F>& r, const Jac<F>& p, const 
 }
 
 // general Jacobian addition (handles infinity, doubling, inverse)
-template <class F> B200_HD void jac_add(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
+template <class F> B200_BIG void jac_add(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
     if (jac_is_inf(p)) { r = q; return; }
     if (jac_is_inf(q)) { r = p; return; }
     F z1z1, z2z2, u1, u2, s1, s2, h, rr, t;
@@ -161,7 +161,7 @@ template <class F> B200_HD void jac_add(Jac<F>& r, const Jac<F>& p, const Jac<F>
     r.x = x3;
 }
 
-template <class F> B200_HD void jac_to_aff(Aff<F>& a, const Jac<F>& p) {
+template <class F> B200_BIG void jac_to_aff(Aff<F>& a, const Jac<F>& p) {
     if (jac_is_inf(p)) { a.inf = 1; a.x = f_zero<F>(); a.y = f_zero<F>(); return; }
     F zi, zi2, zi3;
     f_inv(zi, p.z);
@@ -184,7 +184,7 @@ template <class F> B200_HD bool jac_eq_aff(const Jac<F>& p, const F& qx, const F
 }
 
 // r = [k] * (qx, qy) for a 64-bit scalar, left-to-right double-and-add (k != 0)
-template <class F> B200_HD void jac_mul_u64(Jac<F>& r, const F& qx, const F& qy, uint64_t k) {
+template <class F> B200_BIG void jac_mul_u64(Jac<F>& r, const F& qx, const F& qy, uint64_t k) {
     Jac<F> acc;
     jac_set_inf(acc);
     bool started = false;
@@ -199,7 +199,7 @@ template <class F> B200_HD void jac_mul_u64(Jac<F>& r, const F& qx, const F& qy,
     r = acc;
 }
 // same for a Jacobian base point
-template <class F> B200_HD void jac_mul_u64_jac(Jac<F>& r, const Jac<F>& q, uint64_t k) {
+template <class F> B200_BIG void jac_mul_u64_jac(Jac<F>& r, const Jac<F>& q, uint64_t k) {
     Jac<F> acc;
     jac_set_inf(acc);
     bool started = false;

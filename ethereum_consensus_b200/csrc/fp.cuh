@@ -15,10 +15,18 @@
 
 #if defined(__CUDACC__)
 #define B200_HD __host__ __device__ __forceinline__
-#define B200_HD_NOINLINE __host__ __device__ __noinline__
+#define B200_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define B200_HD inline
-#define B200_HD_NOINLINE
+#define B200_HD_NOINLINE static inline
+#endif
+// B200_BIG: tower / curve-level routines.  Inlined in the wide per-key kernels (limbs stay in registers); real
+// functions (operands in local memory) in the low-parallelism pairing kernels, which keeps their code size and
+// ptxas time bounded.
+#if defined(B200_TOWER_NOINLINE)
+#define B200_BIG B200_HD_NOINLINE
+#else
+#define B200_BIG B200_HD
 #endif
 
 namespace b200 {
@@ -100,7 +108,12 @@ B200_HD void fp_neg(Fp& r, const Fp& a) {
 B200_HD void fp_dbl(Fp& r, const Fp& a) { fp_add(r, a, a); }
 
 // Montgomery product r = a*b/R mod p (CIOS, operand scanning).  Portable C++: identical on host and device.
-B200_HD void fp_mul(Fp& r, const Fp& a, const Fp& b) {
+#if defined(B200_FP_MUL_NOINLINE)
+B200_HD_NOINLINE
+#else
+B200_HD
+#endif
+void fp_mul(Fp& r, const Fp& a, const Fp& b) {
     const Fp p = fp_p();
     uint32_t t[14];
 #pragma unroll
@@ -196,7 +209,7 @@ static const uint32_t h_exp_p_minus_1_div_2[12] = B200_EXP_P_MINUS_1_DIV_2;
 #endif
 
 // r = a^e, e given as 12 little-endian words; left-to-right binary (a != secret: variable time is fine here).
-B200_HD void fp_pow(Fp& r, const Fp& a, const uint32_t* e) {
+B200_BIG void fp_pow(Fp& r, const Fp& a, const uint32_t* e) {
     Fp acc = fp_one();
     bool started = false;
 #pragma unroll 1

@@ -22,7 +22,7 @@ B200_HD void fp6_mul_v(Fp6& r, const Fp6& a) {
     fp2_mul_xi(t, a.c2);
     r.c2 = a.c1; r.c1 = a.c0; r.c0 = t;
 }
-B200_HD void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
+B200_BIG void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
     Fp2 v0, v1, v2, t0, t1, x0, x1, x2;
     fp2_mul(v0, a.c0, b.c0);
     fp2_mul(v1, a.c1, b.c1);
@@ -36,7 +36,7 @@ B200_HD void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
     r.c0 = x0; r.c1 = x1; r.c2 = x2;
 }
 // a * (b0 + b1 v)
-B200_HD void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
+B200_BIG void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
     Fp2 v0, v1, t0, t1, x0, x1, x2;
     fp2_mul(v0, a.c0, b0);
     fp2_mul(v1, a.c1, b1);
@@ -49,14 +49,14 @@ B200_HD void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
     r.c0 = x0; r.c1 = x1; r.c2 = x2;
 }
 // a * (b1 v)
-B200_HD void fp6_mul_by_1(Fp6& r, const Fp6& a, const Fp2& b1) {
+B200_BIG void fp6_mul_by_1(Fp6& r, const Fp6& a, const Fp2& b1) {
     Fp2 x0, x1, x2;
     fp2_mul(x0, a.c2, b1); fp2_mul_xi(x0, x0);
     fp2_mul(x1, a.c0, b1);
     fp2_mul(x2, a.c1, b1);
     r.c0 = x0; r.c1 = x1; r.c2 = x2;
 }
-B200_HD void fp6_inv(Fp6& r, const Fp6& a) {
+B200_BIG void fp6_inv(Fp6& r, const Fp6& a) {
     Fp2 c0, c1, c2, t, d;
     fp2_sqr(c0, a.c0); fp2_mul(t, a.c1, a.c2); fp2_mul_xi(t, t); fp2_sub(c0, c0, t);
     fp2_sqr(c1, a.c2); fp2_mul_xi(c1, c1); fp2_mul(t, a.c0, a.c1); fp2_sub(c1, c1, t);
@@ -78,7 +78,7 @@ B200_HD bool fp12_is_one(const Fp12& a) {
            fp2_is_zero(a.c1.c1) && fp2_is_zero(a.c1.c2);
 }
 B200_HD void fp12_conj(Fp12& r, const Fp12& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
-B200_HD void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
+B200_BIG void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
     Fp6 v0, v1, t0, t1, x1;
     fp6_mul(v0, a.c0, b.c0);
     fp6_mul(v1, a.c1, b.c1);
@@ -91,7 +91,7 @@ B200_HD void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
     fp6_add(r.c0, v0, t0);
     r.c1 = x1;
 }
-B200_HD void fp12_sqr(Fp12& r, const Fp12& a) {
+B200_BIG void fp12_sqr(Fp12& r, const Fp12& a) {
     Fp6 ab, t0, t1, x0;
     fp6_mul(ab, a.c0, a.c1);
     fp6_add(t0, a.c0, a.c1);
@@ -104,7 +104,7 @@ B200_HD void fp12_sqr(Fp12& r, const Fp12& a) {
     fp6_dbl(r.c1, ab);
 }
 // f * (A + B v + C v w): the sparse line value of the M-twist Miller loop (13 Fp2 products)
-B200_HD void fp12_mul_by_line(Fp12& r, const Fp12& f, const Fp2& A, const Fp2& B, const Fp2& C) {
+B200_BIG void fp12_mul_by_line(Fp12& r, const Fp12& f, const Fp2& A, const Fp2& B, const Fp2& C) {
     Fp6 v0, v1, t0, x1;
     Fp2 bc;
     fp6_mul_by_01(v0, f.c0, A, B);
@@ -118,7 +118,7 @@ B200_HD void fp12_mul_by_line(Fp12& r, const Fp12& f, const Fp2& A, const Fp2& B
     fp6_add(r.c0, v0, t0);
     r.c1 = x1;
 }
-B200_HD void fp12_inv(Fp12& r, const Fp12& a) {
+B200_BIG void fp12_inv(Fp12& r, const Fp12& a) {
     Fp6 t0, t1;
     fp6_mul(t0, a.c0, a.c0);
     fp6_mul(t1, a.c1, a.c1);
@@ -151,7 +151,7 @@ template <int K> B200_HD void frob_coeff(Fp2& dst, const Fp2& src, int i) {
     const Fp2 g = frob_gamma<K>(i);
     fp2_mul(dst, t, g);
 }
-template <int K> B200_HD void fp12_frobenius(Fp12& r, const Fp12& a) {
+template <int K> B200_BIG void fp12_frobenius(Fp12& r, const Fp12& a) {
     // w-power index of each tower slot: c0.c0 -> 0, c1.c0 -> 1, c0.c1 -> 2, c1.c1 -> 3, c0.c2 -> 4, c1.c2 -> 5
     frob_coeff<K>(r.c0.c0, a.c0.c0, 0);
     frob_coeff<K>(r.c1.c0, a.c1.c0, 1);

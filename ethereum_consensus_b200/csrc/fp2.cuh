@@ -58,7 +58,7 @@ B200_HD void fp2_mul_xi(Fp2& r, const Fp2& a) {
     fp_add(t1, a.c0, a.c1);
     r.c0 = t0; r.c1 = t1;
 }
-B200_HD void fp2_inv(Fp2& r, const Fp2& a) {
+B200_BIG void fp2_inv(Fp2& r, const Fp2& a) {
     Fp n, t;
     fp_sqr(n, a.c0);
     fp_sqr(t, a.c1);
@@ -68,7 +68,7 @@ B200_HD void fp2_inv(Fp2& r, const Fp2& a) {
     fp_mul(t, a.c1, n);
     fp_neg(r.c1, t);
 }
-B200_HD void fp2_pow(Fp2& r, const Fp2& a, const uint32_t* e) {
+B200_BIG void fp2_pow(Fp2& r, const Fp2& a, const uint32_t* e) {
     Fp2 acc = fp2_one();
     bool started = false;
 #pragma unroll 1
@@ -85,7 +85,7 @@ B200_HD void fp2_pow(Fp2& r, const Fp2& a, const uint32_t* e) {
     r = acc;
 }
 // Square root for p = 3 (mod 4) (Adj & Rodriguez-Henriquez, Alg. 9); returns false if `a` is a non-residue.
-B200_HD bool fp2_sqrt(Fp2& r, const Fp2& a) {
+B200_BIG bool fp2_sqrt(Fp2& r, const Fp2& a) {
     if (fp2_is_zero(a)) { r = a; return true; }
     Fp2 a1, alpha, x0, x, chk;
     fp2_pow(a1, a, B200_EXP_TABLE(exp_p_minus_3_div_4));

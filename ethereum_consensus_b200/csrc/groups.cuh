@@ -86,7 +86,7 @@ B200_HD void g1_compress(uint8_t out[48], const G1Aff& a) {
     if (fp_is_lex_largest(a.y)) out[0] |= 0x20;
 }
 
-B200_HD int32_t g2_uncompress(G2Aff& out, const uint8_t b[96]) {
+B200_BIG int32_t g2_uncompress(G2Aff& out, const uint8_t b[96]) {
     const uint8_t f = b[0];
     out.inf = 0;
     if (!(f & 0x80)) return BLS_BAD_ENCODING;
@@ -119,7 +119,7 @@ B200_HD void g2_compress(uint8_t out[96], const G2Aff& a) {
 }
 
 // psi = twist^-1 o frobenius o twist on Jacobian coordinates: (conj(X)*cx, conj(Y)*cy, conj(Z))
-B200_HD void g2_psi(G2Jac& r, const G2Jac& p) {
+B200_BIG void g2_psi(G2Jac& r, const G2Jac& p) {
     const Fp2 cx = B200_FP2_PSI_X, cy = B200_FP2_PSI_Y;
     Fp2 t;
     fp2_conj(t, p.x); fp2_mul(r.x, t, cx);
@@ -135,7 +135,7 @@ B200_HD void g2_psi2(G2Jac& r, const G2Jac& p) {
 }
 
 // psi(Q) == [z]Q, z = -|z|  (Scott 2021)
-B200_HD bool g2_in_subgroup(const G2Aff& q) {
+B200_BIG bool g2_in_subgroup(const G2Aff& q) {
     if (q.inf) return true;
     G2Jac t, qj, ps;
     jac_mul_u64(t, q.x, q.y, B200_Z_ABS);  // [|z|]Q
@@ -147,7 +147,7 @@ B200_HD bool g2_in_subgroup(const G2Aff& q) {
 }
 
 // h_eff * P via Budroni-Pintore (RFC 9380 G.3); equality with the scalar h_eff is asserted in the generator
-B200_HD void g2_clear_cofactor(G2Jac& r, const G2Jac& p) {
+B200_BIG void g2_clear_cofactor(G2Jac& r, const G2Jac& p) {
     G2Jac t1, t2, t3, np;
     jac_mul_u64_jac(t1, p, B200_Z_ABS);
     jac_neg(t1, t1);                 // t1 = [z]P

@@ -30,7 +30,7 @@ B200_HD void fp_from_be64_mod_p(Fp& r, const uint8_t* b) {
 }
 
 // hash_to_field(msg, count = 2) over Fp2: u0 = e0 + e1 u, u1 = e2 + e3 u
-B200_HD void hash_to_field_fp2(Fp2& u0, Fp2& u1, const uint8_t* msg, size_t len) {
+B200_BIG void hash_to_field_fp2(Fp2& u0, Fp2& u1, const uint8_t* msg, size_t len) {
     uint8_t dstp[44], b0[32], bi[32], tmp[32];
     bls_dst_prime(dstp);
     Sha256Ctx c;
@@ -72,7 +72,7 @@ B200_HD void sswu_g(Fp2& r, const Fp2& x) {
     fp2_add(r, t, B);
 }
 // simplified SWU: t -> (x, y) on E''
-B200_HD void sswu_map(Fp2& x, Fp2& y, const Fp2& t) {
+B200_BIG void sswu_map(Fp2& x, Fp2& y, const Fp2& t) {
     const Fp2 Zc = B200_FP2_SSWU_Z;
     Fp2 t2, zt2, tv1, x1, gx, yy;
     fp2_sqr(t2, t);
@@ -107,7 +107,7 @@ B200_HD void sswu_map(Fp2& x, Fp2& y, const Fp2& t) {
     { const Fp2 k0 = c0, k1 = c1, k2 = c2; r = k2; fp2_mul(r, r, x); fp2_add(r, r, k1); fp2_mul(r, r, x); fp2_add(r, r, k0); }
 
 // 3-isogeny E'' -> E', output in Jacobian coordinates (no inversion): Z = xd*yd
-B200_HD void iso3_map(G2Jac& out, const Fp2& x, const Fp2& y) {
+B200_BIG void iso3_map(G2Jac& out, const Fp2& x, const Fp2& y) {
     Fp2 xn, xd, yn, yd, t, yd2;
     B200_HORNER4(xn, x, B200_FP2_ISO_XNUM0, B200_FP2_ISO_XNUM1, B200_FP2_ISO_XNUM2, B200_FP2_ISO_XNUM3);
     B200_HORNER3(xd, x, B200_FP2_ISO_XDEN0, B200_FP2_ISO_XDEN1, B200_FP2_ISO_XDEN2);
@@ -126,7 +126,7 @@ B200_HD void iso3_map(G2Jac& out, const Fp2& x, const Fp2& y) {
 }
 
 // full hash_to_curve -> affine G2 point
-B200_HD void hash_to_g2(G2Aff& out, const uint8_t* msg, size_t len) {
+B200_BIG void hash_to_g2(G2Aff& out, const uint8_t* msg, size_t len) {
     Fp2 u0, u1, x, y;
     hash_to_field_fp2(u0, u1, msg, len);
     G2Jac q0, q1;

@@ -13,7 +13,7 @@
 
 namespace b200 {
 
-B200_HD void miller_double_step(G2Jac& t, Fp2& A, Fp2& B, Fp2& C, const Fp& xp, const Fp& yp) {
+B200_BIG void miller_double_step(G2Jac& t, Fp2& A, Fp2& B, Fp2& C, const Fp& xp, const Fp& yp) {
     Fp2 xx, yy, zz, e, tmp;
     fp2_sqr(xx, t.x);
     fp2_sqr(yy, t.y);
@@ -31,7 +31,7 @@ B200_HD void miller_double_step(G2Jac& t, Fp2& A, Fp2& B, Fp2& C, const Fp& xp, 
     fp2_mul_fp(C, tmp, yp);        // Z3 Z^2 yP
 }
 
-B200_HD void miller_add_step(G2Jac& t, Fp2& A, Fp2& B, Fp2& C, const G2Aff& q, const Fp& xp, const Fp& yp) {
+B200_BIG void miller_add_step(G2Jac& t, Fp2& A, Fp2& B, Fp2& C, const G2Aff& q, const Fp& xp, const Fp& yp) {
     Fp2 zz, zzz, h, rr, hh, hhh, v, x3, tmp, z3;
     fp2_sqr(zz, t.z);
     fp2_mul(zzz, zz, t.z);
@@ -62,7 +62,7 @@ B200_HD void miller_add_step(G2Jac& t, Fp2& A, Fp2& B, Fp2& C, const G2Aff& q, c
 }
 
 // f_{z,Q}(P); 1 if either point is the point at infinity
-B200_HD void miller_loop(Fp12& f, const G1Aff& p, const G2Aff& q) {
+B200_BIG void miller_loop(Fp12& f, const G1Aff& p, const G2Aff& q) {
     f = fp12_one();
     if (p.inf || q.inf) return;
     G2Jac t;
@@ -85,7 +85,7 @@ B200_HD void miller_loop(Fp12& f, const G1Aff& p, const G2Aff& q) {
 }
 
 // g^|z| by square-and-multiply
-B200_HD void fp12_pow_z(Fp12& r, const Fp12& g) {
+B200_BIG void fp12_pow_z(Fp12& r, const Fp12& g) {
     Fp12 acc = g;
     const uint64_t z = B200_Z_ABS;
 #pragma unroll 1
@@ -97,7 +97,7 @@ B200_HD void fp12_pow_z(Fp12& r, const Fp12& g) {
 }
 
 // f^((p^12-1)/r * 3) == 1 ?
-B200_HD bool final_exp_is_one(const Fp12& f_in) {
+B200_BIG bool final_exp_is_one(const Fp12& f_in) {
     Fp12 f, t0, t1, a, b, c;
     // easy part: f^((p^6-1)(p^2+1))
     fp12_inv(t0, f_in);

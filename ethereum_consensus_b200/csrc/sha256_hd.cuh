@@ -29,7 +29,7 @@ B200_HD uint32_t sha_k(int i) {
 }
 B200_HD uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
-B200_HD void sha_compress(uint32_t st[8], const uint8_t blk[64]) {
+B200_BIG void sha_compress(uint32_t st[8], const uint8_t blk[64]) {
     uint32_t w[64];
     for (int i = 0; i < 16; i++)
         w[i] = (uint32_t(blk[4 * i]) << 24) | (uint32_t(blk[4 * i + 1]) << 16) | (uint32_t(blk[4 * i + 2]) << 8) | blk[4 * i + 3];

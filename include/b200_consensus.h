@@ -103,6 +103,47 @@ B200_API int32_t b200_htr_beacon_state_deneb_shard(const uint8_t* ssz, size_t le
 B200_API int32_t b200_htr_beacon_state_deneb_combine(const uint8_t* ssz, size_t len, int32_t preset, int32_t world,
                                             const uint8_t* all_roots /* world*5*32 */, uint8_t out[32]);
 
+/* ---- BLS12-381 signatures, min-pk (replaces the blst calls of crypto/bls.rs) ------------------------- */
+/* Public keys are 48-byte and signatures 96-byte ZCash-compressed points (crypto/bls.rs:23-25,227-239,287-290);
+ * the ciphersuite / DST is the one at crypto/bls.rs:22.  Results: 0 = Ok(()), 5 = Err(InvalidSignature),
+ * 1,2,3,6 = Err(Error::BLST(..)) from key_validate / Signature::from_bytes, first offending input in order. */
+
+/* verify_signature — crypto/bls.rs:64-77 */
+B200_API int32_t b200_verify_signature(const uint8_t pk[48], const uint8_t* msg, size_t msg_len, const uint8_t sig[96]);
+/* fast_aggregate_verify — crypto/bls.rs:114-132; `pks` is the array of K pointers the reference passes
+ * (`&[&PublicKey]`, gathered from state.validators at phase0/helpers.rs:123-131) */
+B200_API int32_t b200_fast_aggregate_verify(const uint8_t* const* pks, size_t k, const uint8_t* msg, size_t msg_len,
+                                            const uint8_t sig[96]);
+/* eth_fast_aggregate_verify — crypto/bls.rs:150-160 */
+B200_API int32_t b200_eth_fast_aggregate_verify(const uint8_t* const* pks, size_t k, const uint8_t* msg, size_t msg_len,
+                                                const uint8_t sig[96]);
+/* aggregate_verify — crypto/bls.rs:95-112; n_pks x 48 contiguous bytes, n_msgs (pointer,length) messages */
+B200_API int32_t b200_aggregate_verify(const uint8_t* pks_flat, size_t n_pks, const uint8_t* const* msgs,
+                                       const size_t* msg_lens, size_t n_msgs, const uint8_t sig[96]);
+/* aggregate — crypto/bls.rs:79-93; n == 0 -> B200_EMPTY_AGGREGATE; out = compressed sum */
+B200_API int32_t b200_aggregate(const uint8_t* sigs_flat, size_t n, uint8_t out[96]);
+/* eth_aggregate_public_keys — crypto/bls.rs:135-148 */
+B200_API int32_t b200_eth_aggregate_public_keys(const uint8_t* pks_flat, size_t n, uint8_t out[48]);
+
+/* The throughput path: T independent fast_aggregate_verify tuples in one call (the batch of attestation checks
+ * `process_block` issues one by one at deneb/block_processing.rs:104-108).  Tuple t uses public keys
+ * pk_offsets[t] .. pk_offsets[t+1] of `pks_flat`, the 32-byte signing root msgs32[32t..] and sigs[96t..];
+ * out_codes[t] is exactly what b200_fast_aggregate_verify would return for that tuple (strict mode: every key is
+ * decompressed and validated in every call, as crypto/bls.rs:119-123 does). */
+B200_API int32_t b200_fast_aggregate_verify_batch(const uint8_t* pks_flat, const uint32_t* pk_offsets, const uint8_t* msgs32,
+                                                  const uint8_t* sigs, size_t n_tuples, int32_t* out_codes);
+/* Registry mode: validate the (append-only, immutable-pubkey) validator registry once, keep the affine keys in
+ * HBM, then verify tuples that name their signers by validator index.  Same per-tuple codes as the strict path. */
+B200_API int32_t b200_registry_load(const uint8_t* pks_flat, size_t n);
+B200_API int32_t b200_registry_key_codes(int32_t* out_codes, size_t n);
+B200_API int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indices, const uint32_t* offsets,
+                                                          const uint8_t* msgs32, const uint8_t* sigs, size_t n_tuples,
+                                                          int32_t* out_codes);
+/* Device time (ms) of the dominant kernel (per-key validation) of the last BLS call. */
+B200_API float b200_last_dominant_kernel_ms(void);
+/* On-device self-test of the field arithmetic over `n` pseudo-random triples; *mismatches must come back 0. */
+B200_API int32_t b200_fp_selftest(uint32_t n, uint32_t seed, uint32_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

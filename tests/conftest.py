@@ -43,3 +43,18 @@ def engine():
     """The CUDA library bound to cuda:0 — fails loudly (no CPU fallback) if it cannot initialise."""
     from ethereum_consensus_b200 import _lib
     return _lib.init(int(os.environ.get("LOCAL_RANK", "0")))
+
+
+@pytest.fixture(scope="session")
+def host_math():
+    """The product's __host__ __device__ BLS math compiled for the CPU (tests/host_math/host_math.cpp)."""
+    src = ROOT / "tests" / "host_math" / "host_math.cpp"
+    lib = ROOT / "tests" / "host_math" / "libhost_math.so"
+    deps = [src] + list((ROOT / "ethereum_consensus_b200" / "csrc").glob("*.cuh"))
+    if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-o", str(lib), str(src)], check=True)
+    L = ctypes.CDLL(str(lib))
+    L.hm_fast_aggregate_verify.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    L.hm_hash_to_g2.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    L.hm_hash_to_field.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+    return L

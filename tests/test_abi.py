@@ -34,7 +34,9 @@ def test_no_cpu_fallback_without_gpu():
 
 
 def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may import, link or dlopen anything under oracle/."""
+    pat = re.compile(r"(^|\s)(import|from)\s+oracle\b|liboracle|oracle/|#include\s+\".*oracle")
     pkg = ROOT / "ethereum_consensus_b200"
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
-        txt = p.read_text()
-        assert "oracle" not in txt.replace("to_oracle_value", "").replace("oracle's", "").lower() or p.name == "state.py", p
+        for line in p.read_text().splitlines():
+            assert not pat.search(line), (p, line)

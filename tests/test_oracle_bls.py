@@ -1,0 +1,114 @@
+"""CPU: pins the BLS oracle to the reference's own KATs, then checks the product's host-compiled math against it."""
+import ctypes as C
+import json
+import random
+from pathlib import Path
+
+import pytest
+
+from oracle import bls_oracle as bo
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "bls_cases.json").read_text())
+F1, F2 = bo.F1, bo.F2
+
+# KAT B-2: /root/reference/ethereum-consensus/src/crypto/bls.rs:530-544 (`test_can_sign`)
+B2_SK = int("40094c5c6c378857eac09b8ec64c87182f58700c056a8b371ad0eb0a5b983d50", 16)
+B2_MSG = b"blst is such a blast"
+B2_SIG = bytes.fromhex("a01e49276730e4752eef31b0570c8707de501398dac70dd144438cd1bd05fb9b9bb3e1a9ceef0a68cc08904362cafa3f"
+                       "1005e5b699a41847fff6f5552260468846de5bdbf94a9aedeb29bc6cdb2c1d34922d9e9af4c0593a69ae978a90b5aba6")
+# KAT B-1: /root/reference/ethereum-consensus/src/bin/ec/validator/keystores.rs:239-249 (EIP-2335)
+B1_SK = int("000000000019d6689c085ae165831e934ff763ae46a2a6c172b3f1b60a8ce26f", 16)
+B1_PK = bytes.fromhex("9612d7a727c9d0a22e185a1c768478dfe919cada9266988cb32359c11f2b7b27f4ae4040902382ae2910c15e2b420d07")
+# KAT B-2b: decode-only points, crypto/bls.rs:381-390 and :453-461
+GOOD_SIG = bytes.fromhex("abb0124c7574f281a293f4185cad3cb22681d520917ce46665243eacb051000d8bacf75e1451870ca6b3b9e6c9d41a7b"
+                         "02ead2685a84188a4fafd3825daf6a989625d719ccd2d83a40101f4a453fca62878c890eca622363f9ddb8f367a91e84")
+GOOD_PK = bytes.fromhex("a99a76ed7796f7be22d5b7e85deeb7c5677e88e511e0b337618f8c4eb61349b4bf2d153f649f7b53359fe8b94a38e44c")
+
+
+def test_kat_b1_sk_to_pk():
+    assert bo.sk_to_pk(B1_SK) == B1_PK
+
+
+def test_kat_b2_sign_and_verify():
+    assert bo.sign(B2_SK, B2_MSG) == B2_SIG
+    pk = bo.sk_to_pk(B2_SK)
+    assert bo.verify_signature(pk, B2_MSG, B2_SIG) == bo.SUCCESS
+    assert bo.verify_signature(pk, B2_MSG + b"!", B2_SIG) == bo.VERIFY_FAIL
+    assert bo.verify_signature(B1_PK, B2_MSG, B2_SIG) == bo.VERIFY_FAIL
+
+
+def test_kat_b2b_decode_only_points():
+    code, pt = bo.g2_uncompress(GOOD_SIG)
+    assert code == 0 and bo.on_curve(F2, pt) and bo.g2_compress(pt) == GOOD_SIG
+    assert bo.key_validate(GOOD_PK)[0] == 0
+
+
+def test_curve_constants():
+    assert bo.on_curve(F1, bo.G1_GEN) and bo.on_curve(F2, bo.G2_GEN)
+    assert bo.in_subgroup(F1, bo.G1_GEN) and bo.in_subgroup(F2, bo.G2_GEN)
+    z = -bo.Z_ABS
+    assert bo.R == z ** 4 - z ** 2 + 1 and bo.P == (z - 1) ** 2 * bo.R // 3 + z
+
+
+def test_pairing_bilinear_nondegenerate():
+    a, b = 0xdeadbeef, 0xfeedface
+    aP = bo.pt_to_affine(F1, bo.pt_mul(F1, bo.pt_from_affine(F1, bo.G1_GEN), a))
+    bQ = bo.pt_to_affine(F2, bo.pt_mul(F2, bo.pt_from_affine(F2, bo.G2_GEN), b))
+    mabP = bo.pt_to_affine(F1, bo.pt_mul(F1, bo.pt_from_affine(F1, bo.G1_GEN), bo.R - a * b % bo.R))
+    assert bo.pairing_check([(aP, bQ), (mabP, bo.G2_GEN)])
+    assert not bo.pairing_check([(bo.G1_GEN, bo.G2_GEN)])
+
+
+def test_golden_file_matches_oracle_spotcheck():
+    for c in GOLDEN["fast_aggregate_verify"]:
+        if len(c["pks"]) <= 4:
+            got = bo.fast_aggregate_verify([bytes.fromhex(p) for p in c["pks"]], bytes.fromhex(c["msg"]), bytes.fromhex(c["sig"]))
+            assert got == c["code"], c["name"]
+
+
+def _b48(x): return x.to_bytes(48, "big")
+
+
+def test_host_math_fields_match_oracle(host_math):
+    rnd = random.Random(7)
+    out = C.create_string_buffer(48)
+    for i in range(300):
+        a, b = rnd.randrange(bo.P), rnd.randrange(bo.P)
+        if i == 0: a, b = 0, 0
+        if i == 1: a, b = bo.P - 1, bo.P - 1
+        for op, want in ((0, (a + b) % bo.P), (1, (a - b) % bo.P), (2, a * b % bo.P), (5, -a % bo.P)):
+            host_math.hm_fp_op(op, _b48(a), _b48(b), out)
+            assert int.from_bytes(out.raw, "big") == want
+    out = C.create_string_buffer(96)
+    for i in range(20):
+        a = (rnd.randrange(bo.P), rnd.randrange(bo.P)); b = (rnd.randrange(bo.P), rnd.randrange(bo.P))
+        enc = lambda v: _b48(v[0]) + _b48(v[1])  # noqa: E731
+        dec = lambda o: (int.from_bytes(o.raw[:48], "big"), int.from_bytes(o.raw[48:], "big"))  # noqa: E731
+        host_math.hm_fp2_op(0, enc(a), enc(b), out); assert dec(out) == bo.f2_mul(a, b)
+        host_math.hm_fp2_op(2, enc(a), enc(b), out); assert dec(out) == bo.f2_inv(a)
+        ok = host_math.hm_fp2_op(3, enc(a), enc(b), out); assert bool(ok) == (bo.f2_sqrt(a) is not None)
+        assert host_math.hm_fp2_op(4, enc(a), enc(b), out) == bo.f2_sgn0(a)
+    assert host_math.hm_fp12_selftest() == 31
+
+
+def test_host_math_hash_to_g2_matches_oracle(host_math):
+    o = C.create_string_buffer(192); inf = C.c_int()
+    for m in (b"", b"abc", B2_MSG, bytes(32), bytes(range(100)), bytes(255)):
+        host_math.hm_hash_to_g2(m, len(m), o, C.byref(inf))
+        pt = ((int.from_bytes(o.raw[0:48], "big"), int.from_bytes(o.raw[48:96], "big")),
+              (int.from_bytes(o.raw[96:144], "big"), int.from_bytes(o.raw[144:], "big")))
+        assert inf.value == 0 and pt == bo.hash_to_g2(m)
+
+
+def test_host_math_kat_b2(host_math):
+    pk = bo.sk_to_pk(B2_SK)
+    assert host_math.hm_fast_aggregate_verify(pk, 1, B2_MSG, len(B2_MSG), B2_SIG) == 0
+    assert host_math.hm_fast_aggregate_verify(pk, 1, B2_MSG + b"!", len(B2_MSG) + 1, B2_SIG) == 5
+
+
+@pytest.mark.parametrize("case", GOLDEN["fast_aggregate_verify"], ids=lambda c: c["name"])
+def test_host_math_fast_aggregate_verify_golden(host_math, case):
+    """Every golden tuple through the product's own (host-compiled) decode / subgroup / hash / pairing code."""
+    pks = b"".join(bytes.fromhex(p) for p in case["pks"])
+    m, s = bytes.fromhex(case["msg"]), bytes.fromhex(case["sig"])
+    assert host_math.hm_fast_aggregate_verify(pks, len(case["pks"]), m, len(m), s) == case["code"]
