@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's configs.
+
+Headline (configs[1]): `fast_aggregate_verify tuples/s`, mainnet preset, T = 4096 attestation tuples x K = 512 public
+keys per tuple, strict mode (every key decompressed + validated in every call, as
+/root/reference/ethereum-consensus/src/crypto/bls.rs:119-123 does), on 1..N B200 (one process per GPU; tuples shard
+with no data-path collective; the per-shard verdict vectors are exchanged with one NCCL all_gather).
+Secondary (configs[2]), same JSON line under "ssz": `hash_tree_root(BeaconState) ms`, deneb mainnet, 2**20 validators.
+
+One step = one pass of the hot path over one batch.  `value` = device time (CUDA events on the library's launching
+stream, inputs already in HBM); `e2e` = the same batch through the public C-ABI call with pinned HOST buffers,
+H2D + kernels + D2H of the verdicts inside the timed region.  `--impl reference` times the CPU restatement
+(oracle/, plain C; blst/ssz_rs themselves cannot be built offline — DESIGN.md) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+SEED = 0xB200
+# a point of E'(Fp2) outside G2 (iso3(sswu(5+7u)) compressed; produced by oracle/bls_oracle.py, see tests/golden)
+SIG_NOT_IN_GROUP = None  # filled from tests/golden/bls_cases.json
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def load_oracles():
+    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
+    bls = C.CDLL(str(ROOT / "oracle" / "liboracle_bls.so"))
+    ssz = C.CDLL(str(ROOT / "oracle" / "liboracle_ssz.so"))
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+    bls.orc_fast_aggregate_verify_batch.argtypes = [vp, vp, vp, vp, sz, vp, ci]
+    bls.orc_sign_batch.argtypes = [vp, vp, sz, vp, ci]
+    bls.orc_pk_sequence.argtypes = [C.c_char_p, C.c_char_p, sz, vp]
+    bls.orc_fast_aggregate_verify.argtypes = [vp, sz, vp, sz, vp]
+    bls.orc_fp_mul_count.restype = C.c_uint64
+    ssz.orc_htr_beacon_state_deneb.argtypes = [vp, sz, ci, ci, vp]
+    ssz.orc_htr_beacon_state_deneb.restype = ci
+    return bls, ssz
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self._stop, self._th = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), "samples": len(self.rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------ BLS workload
+def make_bls_workload(orc, T: int, K: int, rank: int, n_distinct: int = 1 << 15, n_registry: int = 1 << 20, threads: int = 8):
+    """registry of 2**20 validators (n_distinct distinct keys tiled), T tuples of K signers drawn
+    by a seeded permutation, 32-byte signing roots, aggregate signatures; ~3 % adversarial tuples."""
+    sk0 = int.from_bytes(hashlib.sha256(b"b200/sk0" + SEED.to_bytes(8, "little")).digest(), "big") % R_ORDER
+    delta = int.from_bytes(hashlib.sha256(b"b200/delta" + SEED.to_bytes(8, "little")).digest(), "big") % R_ORDER
+    keys = np.empty((n_distinct, 48), dtype=np.uint8)
+    orc.orc_pk_sequence(sk0.to_bytes(32, "big"), delta.to_bytes(32, "big"), n_distinct, keys.ctypes.data)
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    perm = rng.permutation(n_registry).astype(np.uint32)
+    need = T * K
+    idx = np.resize(perm, need).astype(np.uint32)  # every validator attests need / n_registry times
+    off = (np.arange(T + 1, dtype=np.uint64) * K).astype(np.uint32)
+    msgs = np.frombuffer(b"".join(hashlib.sha256(b"b200/msg" + SEED.to_bytes(8, "little") + (rank << 32 | t).to_bytes(8, "little")).digest()
+                                  for t in range(T)), dtype=np.uint8).copy().reshape(T, 32)
+    kd = (idx % n_distinct).reshape(T, K).astype(object)
+    kind = np.zeros(T, dtype=np.int32)  # 0 valid, 1 wrong msg, 2 signer missing, 3 sig not in group, 4 pk infinity, 5 keys cancel
+    u = rng.random(T)
+    kind[u < 0.01] = 1
+    kind[(u >= 0.01) & (u < 0.02)] = 2
+    kind[(u >= 0.02) & (u < 0.025)] = 3
+    kind[(u >= 0.025) & (u < 0.0275)] = 4
+    kind[(u >= 0.0275) & (u < 0.03)] = 5
+    sks = np.empty((T, 32), dtype=np.uint8)
+    for t in range(T):
+        row = kd[t]
+        s = (K * sk0 + delta * int(row.sum())) % R_ORDER
+        if kind[t] == 2:
+            s = (s - (sk0 + delta * int(row[-1]))) % R_ORDER
+        sks[t] = np.frombuffer((s if s else 1).to_bytes(32, "big"), dtype=np.uint8)
+    sign_msgs = msgs.copy()
+    sign_msgs[kind == 1] ^= 0x55  # signature made over a different root
+    sigs = np.empty((T, 96), dtype=np.uint8)
+    orc.orc_sign_batch(sks.ctypes.data, sign_msgs.ctypes.data, T, sigs.ctypes.data, threads)
+    cases = json.loads((ROOT / "tests" / "golden" / "bls_cases.json").read_text())["fast_aggregate_verify"]
+    bad_sig = next(bytes.fromhex(c["sig"]) for c in cases if c["name"] == "signature not in subgroup")
+    sigs[kind == 3] = np.frombuffer(bad_sig, dtype=np.uint8)
+    flat = keys[idx % n_distinct].reshape(T, K, 48).copy()
+    inf_pk = np.zeros(48, dtype=np.uint8); inf_pk[0] = 0xC0
+    for t in np.nonzero(kind == 4)[0]:
+        flat[t, K // 3] = inf_pk
+    for t in np.nonzero(kind == 5)[0]:  # K/2 pairs (P, -P): the aggregate key is the point at infinity
+        half = flat[t, : K // 2].copy()
+        neg = half.copy(); neg[:, 0] ^= 0x20
+        flat[t, : K // 2] = half; flat[t, K // 2: 2 * (K // 2)] = neg
+    expect = np.select([kind == 0, kind == 4], [0, 6], default=5).astype(np.int32)
+    registry = np.tile(keys, (n_registry // n_distinct, 1))
+    return {"pks": flat.reshape(-1), "off": off, "msgs": msgs.reshape(-1), "sigs": sigs.reshape(-1), "expect": expect, "kind": kind,
+            "idx": idx, "registry": registry.reshape(-1), "T": T, "K": K}
+
+
+def pin(arr):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tuples", type=int, default=4096)
+    ap.add_argument("--keys", type=int, default=512)
+    ap.add_argument("--validators", type=int, default=1 << 20)
+    ap.add_argument("--skip-ssz", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    host_threads = os.cpu_count() or 1
+    T, K = args.tuples, args.keys
+    workload = f"mainnet preset: batch {T} Attestation fast_aggregate_verify tuples, K={K} pubkeys/tuple, strict per-key validation"
+    base = {"metric": "fast_aggregate_verify tuples/s", "unit": "tuples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp), u32 SHA-256 words",
+            "data": "synthetic",
+            "config": {"workload": workload, "tuples_per_gpu": T, "keys_per_tuple": K, "registry": 1 << 20, "mode": "strict",
+                       "adversarial_fraction": 0.03, "l2": "256 MiB memset between timed steps (flush)", "parallelism": f"tuples sharded x{world}"}}
+
+    orc_bls, orc_ssz = load_oracles()
+
+    # ---------------------------------------------------------------- reference arm: CPU restatement on host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = min(T, 8 * host_threads)
+        w = make_bls_workload(orc_bls, sample, K, 0, threads=host_threads)
+        out = np.empty(sample, dtype=np.int32)
+        times = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            orc_bls.orc_fast_aggregate_verify_batch(w["pks"].ctypes.data, w["off"].ctypes.data, w["msgs"].ctypes.data, w["sigs"].ctypes.data,
+                                                    sample, out.ctypes.data, host_threads)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+        assert out.tolist() == w["expect"].tolist(), "CPU restatement disagrees with the constructed verdicts"
+        ms = 1e3 * sum(times) / len(times)
+        v = sample / (ms / 1e3)
+        line = dict(base)
+        line.update({"impl": "reference", "value": v, "ms_per_step": ms, "gpu_launches": 0,
+                     "cpu_baseline": {"value": v, "unit": "tuples/s", "cores": host_threads, "kind": "port",
+                                      "sample": f"{sample} of the {T} tuples per step, all host threads (plain-C restatement, not blst)"},
+                     "e2e": {"value": v, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    from ethereum_consensus_b200 import _lib, crypto, ssz, state as S
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.init(local_rank)
+    lib = _lib.load()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+
+    w = make_bls_workload(orc_bls, T, K, rank, threads=host_threads)
+    pks, off, msgs, sigs = pin(w["pks"]), w["off"], pin(w["msgs"]), pin(w["sigs"])
+    gathered = [torch.empty(T, dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def step():
+        codes = crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs)
+        if world > 1:  # the path's one exchange step: every rank learns every shard's verdicts
+            dist.all_gather(gathered, torch.from_numpy(codes).cuda())
+            torch.cuda.synchronize()
+        return codes
+
+    for _ in range(args.warmup):
+        codes = step()
+    assert codes.tolist() == w["expect"].tolist(), "GPU verdicts differ from the constructed expectation"
+
+    launches0 = lib.b200_launch_count()
+    dev_ms, dom_ms, wall = [], [], []
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t_all0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush_l2()
+            barrier()
+            t0 = time.perf_counter()
+            codes = step()
+            barrier()
+            wall.append(time.perf_counter() - t0)
+            dev_ms.append(crypto.last_kernel_ms())
+            dom_ms.append(crypto.last_dominant_kernel_ms())
+        t_all = time.perf_counter() - t_all0
+    launches = lib.b200_launch_count() - launches0
+    assert codes.tolist() == w["expect"].tolist()
+
+    ms_dev = max_over_ranks(sum(dev_ms) / len(dev_ms))
+    ms_e2e = max_over_ranks(1e3 * sum(wall) / len(wall))
+    value = world * T / (ms_dev / 1e3)
+    e2e_value = world * T / (ms_e2e / 1e3)
+    h2d = int(w["pks"].nbytes + w["msgs"].nbytes + w["sigs"].nbytes + w["off"].nbytes)
+
+    # registry mode (validated keys resident in HBM) — reported separately, never as the headline
+    reg_ms = None
+    try:
+        reg = crypto.Registry(pin(w["registry"]))
+        reg_load_ms = crypto.last_kernel_ms()
+        for _ in range(2):
+            rc = reg.verify_batch(w["idx"], off, msgs, sigs)
+        reg_ms = crypto.last_kernel_ms()
+        # tuples whose bytes were edited (infinity key / cancelling keys) differ by construction in registry mode
+        same = (w["kind"] != 4) & (w["kind"] != 5)
+        assert (rc[same] == w["expect"][same]).all()
+    except Exception as e:  # noqa: BLE001
+        reg_ms, reg_load_ms = None, None
+        print(f"[bench] registry mode skipped: {e}", file=sys.stderr)
+
+    line = dict(base)
+    if rank == 0:
+        # ---- CPU baseline: bounded sample of the same workload on the host cores (all threads) + parity on that sample
+        sample = min(T, 8 * host_threads)
+        out = np.empty(sample, dtype=np.int32)
+        t0 = time.perf_counter()
+        orc_bls.orc_fast_aggregate_verify_batch(w["pks"].ctypes.data, w["off"].ctypes.data, w["msgs"].ctypes.data, w["sigs"].ctypes.data,
+                                                sample, out.ctypes.data, host_threads)
+        cpu_dt = time.perf_counter() - t0
+        assert out.tolist() == codes[:sample].tolist(), "GPU vs CPU-oracle verdict mismatch on the baseline sample"
+        bad = np.nonzero(w["kind"] != 0)[0][:16]  # every adversarial kind, checked against the oracle as well
+        for t in bad:
+            got = orc_bls.orc_fast_aggregate_verify(w["pks"].ctypes.data + int(w["off"][t]) * 48, K, w["msgs"].ctypes.data + 32 * int(t), 32,
+                                                    w["sigs"].ctypes.data + 96 * int(t))
+            assert got == int(codes[t]), (int(t), got, int(codes[t]))
+        t0 = time.perf_counter()
+        orc_bls.orc_fp_mul_count_reset()
+        orc_bls.orc_fast_aggregate_verify(w["pks"].ctypes.data, K, w["msgs"].ctypes.data, 32, w["sigs"].ctypes.data)
+        cpu_1t = time.perf_counter() - t0
+        fp_mul_per_tuple = int(orc_bls.orc_fp_mul_count())
+
+        imad_peak = crypto.measure_int_peak(0)
+        alu_peak = crypto.measure_int_peak(2)
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = sum(dom_ms) / len(dom_ms)
+        alg_bytes = T * (48 * K + 128)
+        line.update({
+            "value": value, "ms_per_step": ms_dev, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "tuples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * T},
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "k_g1_validate", "achieved": alg_bytes / (dom / 1e3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": alg_bytes / (dom / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "note": "algorithmic bytes = T*(48K+128); this path is integer-pipe bound, see int_roofline",
+                         "kernel_ms": dom, "share_of_step": dom / ms_dev},
+            "int_roofline": {"unit": "G 32x32 multiply-adds/s", "fp_mul_per_tuple_cpu_oracle_count": fp_mul_per_tuple,
+                             "achieved": value * fp_mul_per_tuple * 288 / 1e9 / world, "peak": imad_peak,
+                             "frac": value * fp_mul_per_tuple * 288 / 1e9 / world / imad_peak,
+                             "note": "algorithmic Fp products (CPU oracle's instrumented counter for one K-key tuple) x 288 multiply-adds "
+                                     "/ device time, vs the IMAD.WIDE.U32 issue rate measured on this GPU by b200_measure_int_peak(0)",
+                             "alu_lop3_shf_iadd3_peak_gops": alu_peak},
+            "cpu_baseline": {"value": sample / cpu_dt, "unit": "tuples/s", "cores": host_threads, "kind": "port",
+                             "sample": f"first {sample} of the {T} tuples, all {host_threads} host threads; single-thread: {1.0 / cpu_1t:.2f} tuples/s "
+                                       "(plain-C restatement of the reference semantics, not blst)"},
+            "registry_mode": {"ms_per_step": reg_ms, "tuples_per_s": (T / (reg_ms / 1e3)) if reg_ms else None, "registry_load_ms": reg_load_ms},
+            "wall_s_timed_region": t_all,
+        })
+
+    # ---------------------------------------------------------------- secondary: hash_tree_root(BeaconState)
+    if not args.skip_ssz:
+        st = S.synth_state(args.validators, "mainnet")
+        ssz_bytes = S.serialize(st)
+        host = pin(ssz_bytes)
+        golden = json.loads((ROOT / "tests" / "golden" / "ssz_roots.json").read_text()).get("mainnet:1048576:default")
+        if world == 1:
+            dev = ssz.DeviceBeaconState(host, "mainnet")
+            for _ in range(3):
+                root = dev.hash_tree_root()
+            ks = []
+            for _ in range(args.steps):
+                flush_l2()
+                root = dev.hash_tree_root()
+                ks.append(float(lib.b200_last_kernel_ms()))
+            dev.close()
+            es = []
+            for i in range(args.steps + 2):
+                flush_l2()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                root2 = ssz.hash_tree_root_beacon_state(host, "mainnet")
+                dt = time.perf_counter() - t0
+                if i >= 2:
+                    es.append(dt * 1e3)
+            assert root == root2
+        else:
+            ks, es = [], []
+            for i in range(args.steps + 3):
+                flush_l2()
+                barrier()
+                t0 = time.perf_counter()
+                mine = ssz.shard_roots(host, "mainnet", rank, world)
+                tl = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
+                parts = [torch.empty_like(tl) for _ in range(world)]
+                dist.all_gather(parts, tl)
+                allr = b"".join(bytes(p.cpu().numpy()) for p in parts)
+                root = ssz.combine_roots(host, "mainnet", world, allr)
+                barrier()
+                if i >= 3:
+                    es.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+        if args.validators == 1 << 20 and golden:
+            assert root.hex() == golden, "hash_tree_root(BeaconState) differs from the hashlib golden root"
+        if rank == 0:
+            out32 = C.create_string_buffer(32)
+            t0 = time.perf_counter()
+            orc_ssz.orc_htr_beacon_state_deneb(ssz_bytes.ctypes.data, len(ssz_bytes), 0, 1, out32)
+            cpu1 = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            orc_ssz.orc_htr_beacon_state_deneb(ssz_bytes.ctypes.data, len(ssz_bytes), 0, host_threads, out32)
+            cpun = (time.perf_counter() - t0) * 1e3
+            assert out32.raw == root
+            n_hash = 10_117_927 if args.validators == 1 << 20 else None
+            k_ms = (sum(ks) / len(ks)) if ks else None
+            line["ssz"] = {"metric": "hash_tree_root(BeaconState) ms", "validators": args.validators, "root": root.hex(),
+                           "value_ms_device_resident": k_ms, "e2e_ms_from_pinned_host": sum(es) / len(es), "h2d_bytes": int(len(ssz_bytes)),
+                           "scaling": "strong" if world > 1 else None,
+                           "roofline": {"bound": "hbm", "achieved": (n_hash * 96 / (k_ms / 1e3) / 1e9) if (k_ms and n_hash) else None,
+                                        "peak": float(peaks.get("hbm_gbs", 6650.0)) if rank == 0 else None, "unit": "GB/s",
+                                        "frac": (n_hash * 96 / (k_ms / 1e3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))) if (k_ms and n_hash) else None,
+                                        "note": "algorithmic bytes = 10 117 927 pair-hashes x 96 B (SURVEY.md §8d); SHA-256 is ALU-pipe bound",
+                                        "sha256_compressions_per_s": (2 * n_hash / (k_ms / 1e3)) if (k_ms and n_hash) else None},
+                           "cpu_baseline": {"ms_1_thread": cpu1, f"ms_{host_threads}_threads": cpun, "kind": "port",
+                                            "note": "plain-C restatement with SHA-NI when the host has it (not ssz_rs)"}}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

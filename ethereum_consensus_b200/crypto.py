@@ -40,6 +40,7 @@ _lib.register_protos({
     "b200_fast_aggregate_verify_batch_indexed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200_last_dominant_kernel_ms": (C.c_float, []),
     "b200_fp_selftest": (C.c_int32, [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "b200_measure_int_peak": (C.c_int32, [C.c_int32, C.POINTER(C.c_double)]),
 })
 
 
@@ -205,3 +206,10 @@ def fp_selftest(n: int = 1 << 16, seed: int = 1) -> int:
     m = C.c_uint32(0)
     _lib.check(_lib.lib().b200_fp_selftest(n, seed, C.byref(m)), "fp_selftest")
     return int(m.value)
+
+
+def measure_int_peak(kind: int) -> float:
+    """1e9 ops/s of IMAD.WIDE.U32 (0), IMAD.U32 (1) or the LOP3/SHF/IADD3 mix (2) measured on this device."""
+    g = C.c_double(0)
+    _lib.check(_lib.lib().b200_measure_int_peak(kind, C.byref(g)), "measure_int_peak")
+    return float(g.value)

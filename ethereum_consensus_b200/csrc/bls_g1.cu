@@ -104,6 +104,7 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
     Fp a, b, c;
     for (int k = 0; k < 12; k++) { a.l[k] = next(); b.l[k] = next(); c.l[k] = next(); }
     a.l[11] &= 0x0fffffffu; b.l[11] &= 0x0fffffffu; c.l[11] &= 0x0fffffffu;  // < p
+    if ((i & 7) == 1) { const Fp pp = fp_p(); Fp one; for (int k = 0; k < 12; k++) one.l[k] = 0; one.l[0] = 1 + (i >> 3); fp_sub_raw(a, pp, one); }  // near p
     Fp ab, bc, l, r, t;
     uint32_t bad = 0;
     fp_mul(ab, a, b); fp_mul(l, ab, c); fp_mul(bc, b, c); fp_mul(r, a, bc);
@@ -112,6 +113,8 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
     if (!fp_eq(l, r)) bad++;
     fp_sqr(l, a); fp_mul(r, a, a);
     if (!fp_eq(l, r)) bad++;
+    fp_mul_portable(r, a, b);  // tuned PTX product vs the portable one
+    if (!fp_eq(ab, r)) bad++;
     if ((i & 63) == 0 && !fp_is_zero(a)) {
         fp_inv(t, a); fp_mul(t, t, a);
         if (!fp_eq(t, fp_one())) bad++;

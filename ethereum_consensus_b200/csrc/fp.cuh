@@ -108,12 +108,8 @@ B200_HD void fp_neg(Fp& r, const Fp& a) {
 B200_HD void fp_dbl(Fp& r, const Fp& a) { fp_add(r, a, a); }
 
 // Montgomery product r = a*b/R mod p (CIOS, operand scanning).  Portable C++: identical on host and device.
-#if defined(B200_FP_MUL_NOINLINE)
-B200_HD_NOINLINE
-#else
-B200_HD
-#endif
-void fp_mul(Fp& r, const Fp& a, const Fp& b) {
+// Accepts a < 2^384 (not only a < p) as long as b < p: used where an unreduced integer enters the field.
+B200_HD void fp_mul_portable(Fp& r, const Fp& a, const Fp& b) {
     const Fp p = fp_p();
     uint32_t t[14];
 #pragma unroll
@@ -148,6 +144,27 @@ void fp_mul(Fp& r, const Fp& a, const Fp& b) {
     for (int i = 0; i < 12; i++) out.l[i] = t[i];
     fp_reduce_once(out);  // t < 2p
     r = out;
+}
+}  // namespace b200
+#include "fp_mul_ptx.cuh"
+namespace b200 {
+
+// The product used everywhere: on the device the generated inline-PTX sequence (mad.lo.cc/madc.hi.cc pairs that
+// ptxas fuses into IMAD.WIDE.U32.X carry chains, inputs must be < p); on the host the portable code above.
+#if defined(B200_FP_MUL_NOINLINE)
+B200_HD_NOINLINE
+#else
+B200_HD
+#endif
+void fp_mul(Fp& r, const Fp& a, const Fp& b) {
+#if defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE)
+    Fp out;
+    fp_mul_ptx_core(out.l, a.l, b.l);
+    fp_reduce_once(out);
+    r = out;
+#else
+    fp_mul_portable(r, a, b);
+#endif
 }
 B200_HD void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
 

@@ -24,7 +24,7 @@ B200_HD void fp_from_be64_mod_p(Fp& r, const uint8_t* b) {
         hi.l[i] = (uint32_t(q[0]) << 24) | (uint32_t(q[1]) << 16) | (uint32_t(q[2]) << 8) | q[3];
     }
     const Fp r2 = B200_FP_R2, r3 = B200_FP_R3;
-    fp_mul(lo, lo, r2);   // lo * R        (lo < 2^384 = R, so lo*R2 < R*p: valid Montgomery input)
+    fp_mul_portable(lo, lo, r2);   // lo * R  (lo < 2^384 may exceed p: the portable product accepts it)
     fp_mul(t, hi, r3);    // hi * R * R
     fp_add(r, lo, t);
 }

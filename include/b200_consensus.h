@@ -141,6 +141,9 @@ B200_API int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indice
                                                           int32_t* out_codes);
 /* Device time (ms) of the dominant kernel (per-key validation) of the last BLS call. */
 B200_API float b200_last_dominant_kernel_ms(void);
+/* Measured integer-pipe peak on this device, 1e9 ops/s: kind 0 IMAD.WIDE.U32 (Montgomery multiply-add), 1 IMAD.U32,
+ * 2 LOP3/SHF/IADD3 mix (SHA-256 round ops).  Roofline denominators for bench.py. */
+B200_API int32_t b200_measure_int_peak(int32_t kind, double* gops);
 /* On-device self-test of the field arithmetic over `n` pseudo-random triples; *mismatches must come back 0. */
 B200_API int32_t b200_fp_selftest(uint32_t n, uint32_t seed, uint32_t* mismatches);
 

@@ -58,3 +58,28 @@ def host_math():
     L.hm_hash_to_g2.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     L.hm_hash_to_field.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
     return L
+
+
+@pytest.fixture(scope="session")
+def oracle_bls_c():
+    """The plain-C BLS oracle (oracle/c/bls_oracle.c) loaded through ctypes."""
+    _make_oracles()
+    L = ctypes.CDLL(str(ROOT / "oracle" / "liboracle_bls.so"))
+    cp, sz, vp = ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p
+    L.orc_fast_aggregate_verify.argtypes = [cp, sz, cp, sz, cp]
+    L.orc_eth_fast_aggregate_verify.argtypes = [cp, sz, cp, sz, cp]
+    L.orc_verify_signature.argtypes = [cp, cp, sz, cp]
+    L.orc_aggregate_verify.argtypes = [cp, sz, vp, vp, sz, cp]
+    L.orc_aggregate.argtypes = [cp, sz, cp]
+    L.orc_eth_aggregate_public_keys.argtypes = [cp, sz, cp]
+    L.orc_key_validate.argtypes = [cp]
+    L.orc_g1_group_checks_agree.argtypes = [cp]
+    L.orc_g2_group_checks_agree.argtypes = [cp]
+    L.orc_hash_to_g2.argtypes = [cp, sz, cp]
+    L.orc_sk_to_pk.argtypes = [cp, cp]
+    L.orc_sign.argtypes = [cp, cp, sz, cp]
+    L.orc_fast_aggregate_verify_batch.argtypes = [vp, vp, vp, vp, sz, vp, ctypes.c_int]
+    L.orc_sign_batch.argtypes = [vp, vp, sz, vp, ctypes.c_int]
+    L.orc_pk_sequence.argtypes = [cp, cp, sz, vp]
+    L.orc_fp_mul_count.restype = ctypes.c_uint64
+    return L

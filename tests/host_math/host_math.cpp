@@ -158,3 +158,13 @@ HM int hm_fast_aggregate_verify(const uint8_t* pks, size_t k, const uint8_t* msg
 }
 
 }  // extern "C"
+
+// the C emulation of the generated PTX instruction list vs the portable product (raw Montgomery-domain limbs)
+extern "C" HM int hm_fp_mul_emul_matches(const uint32_t* a, const uint32_t* b) {
+    Fp x, y, want, got;
+    for (int i = 0; i < 12; i++) { x.l[i] = a[i]; y.l[i] = b[i]; }
+    fp_mul_portable(want, x, y);
+    fp_mul_emul_core(got.l, x.l, y.l);
+    fp_reduce_once(got);
+    return fp_eq(want, got);
+}

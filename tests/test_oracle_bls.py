@@ -112,3 +112,75 @@ def test_host_math_fast_aggregate_verify_golden(host_math, case):
     pks = b"".join(bytes.fromhex(p) for p in case["pks"])
     m, s = bytes.fromhex(case["msg"]), bytes.fromhex(case["sig"])
     assert host_math.hm_fast_aggregate_verify(pks, len(case["pks"]), m, len(m), s) == case["code"]
+
+
+# ---------------------------------------------------------------------------------------------- the plain-C oracle
+def test_c_oracle_kats(oracle_bls_c):
+    o48, o96 = C.create_string_buffer(48), C.create_string_buffer(96)
+    oracle_bls_c.orc_sk_to_pk(B1_SK.to_bytes(32, "big"), o48)
+    assert o48.raw == B1_PK
+    oracle_bls_c.orc_sign(B2_SK.to_bytes(32, "big"), B2_MSG, len(B2_MSG), o96)
+    assert o96.raw == B2_SIG
+    oracle_bls_c.orc_sk_to_pk(B2_SK.to_bytes(32, "big"), o48)
+    assert oracle_bls_c.orc_verify_signature(o48.raw, B2_MSG, len(B2_MSG), B2_SIG) == 0
+    assert oracle_bls_c.orc_verify_signature(o48.raw, B2_MSG + b"!", len(B2_MSG) + 1, B2_SIG) == 5
+    assert oracle_bls_c.orc_key_validate(GOOD_PK) == 0
+
+
+def test_c_oracle_hash_to_g2_matches_python(oracle_bls_c):
+    o = C.create_string_buffer(192)
+    for m in (b"", b"abc", bytes(32), bytes(range(200))):
+        oracle_bls_c.orc_hash_to_g2(m, len(m), o)
+        pt = ((int.from_bytes(o.raw[0:48], "big"), int.from_bytes(o.raw[48:96], "big")),
+              (int.from_bytes(o.raw[96:144], "big"), int.from_bytes(o.raw[144:], "big")))
+        assert pt == bo.hash_to_g2(m)
+
+
+def test_c_oracle_group_check_shortcuts_agree_with_definition(oracle_bls_c):
+    """phi / psi membership tests vs [r]P == inf on curve points inside and outside the prime-order subgroups."""
+    for x in range(1, 60):
+        for flag in (0x80, 0xA0):
+            assert oracle_bls_c.orc_g1_group_checks_agree(bytes([flag]) + x.to_bytes(48, "big")[1:]) == 1
+            assert oracle_bls_c.orc_g2_group_checks_agree(bytes([flag]) + bytes(47) + x.to_bytes(48, "big")) == 1
+    for c in GOLDEN["fast_aggregate_verify"][:6]:
+        for p in c["pks"]:
+            assert oracle_bls_c.orc_g1_group_checks_agree(bytes.fromhex(p)) == 1
+        assert oracle_bls_c.orc_g2_group_checks_agree(bytes.fromhex(c["sig"])) == 1
+
+
+@pytest.mark.parametrize("case", GOLDEN["fast_aggregate_verify"], ids=lambda c: c["name"])
+def test_c_oracle_fast_aggregate_verify_golden(oracle_bls_c, case):
+    pks = b"".join(bytes.fromhex(p) for p in case["pks"])
+    m, s = bytes.fromhex(case["msg"]), bytes.fromhex(case["sig"])
+    assert oracle_bls_c.orc_fast_aggregate_verify(pks, len(case["pks"]), m, len(m), s) == case["code"]
+
+
+def test_c_oracle_other_entry_points_golden(oracle_bls_c):
+    for c in GOLDEN["aggregate_verify"]:
+        msgs = [bytes.fromhex(m) for m in c["msgs"]]
+        arr = (C.c_char_p * max(len(msgs), 1))(*msgs) if msgs else (C.c_char_p * 1)()
+        lens = (C.c_size_t * max(len(msgs), 1))(*[len(m) for m in msgs])
+        pks = b"".join(bytes.fromhex(p) for p in c["pks"])
+        got = oracle_bls_c.orc_aggregate_verify(pks, len(c["pks"]), C.cast(arr, C.c_void_p), C.cast(lens, C.c_void_p), len(msgs),
+                                                bytes.fromhex(c["sig"]))
+        assert got == c["code"], c["name"]
+    o96, o48 = C.create_string_buffer(96), C.create_string_buffer(48)
+    for c in GOLDEN["aggregate"]:
+        got = oracle_bls_c.orc_aggregate(b"".join(bytes.fromhex(s) for s in c["sigs"]), len(c["sigs"]), o96)
+        assert got == c["code"] and (got != 0 or o96.raw.hex() == c["out"]), c["name"]
+    for c in GOLDEN["eth_aggregate_public_keys"]:
+        got = oracle_bls_c.orc_eth_aggregate_public_keys(b"".join(bytes.fromhex(s) for s in c["pks"]), len(c["pks"]), o48)
+        assert got == c["code"] and (got != 0 or o48.raw.hex() == c["out"]), c["name"]
+    assert oracle_bls_c.orc_aggregate(b"", 0, o96) == 16 and oracle_bls_c.orc_eth_aggregate_public_keys(b"", 0, o48) == 16
+
+
+def test_fp_mul_ptx_emulation(host_math):
+    """The generated inline-PTX Montgomery product, emulated instruction by instruction in C, equals the portable
+    product and the big-int result (tools/gen_fp_mul_ptx.py emits both from one instruction list)."""
+    rnd = random.Random(11)
+    A12 = C.c_uint32 * 12
+    lim = lambda x: A12(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(12)])  # noqa: E731
+    edge = [0, 1, 2, bo.P - 1, bo.P - 2, (1 << 380), (bo.P - 1) // 2, 0xFFFFFFFF]
+    cases = [(a, b) for a in edge for b in edge] + [(rnd.randrange(bo.P), rnd.randrange(bo.P)) for _ in range(20000)]
+    for a, b in cases:
+        assert host_math.hm_fp_mul_emul_matches(lim(a), lim(b)) == 1
