@@ -28,6 +28,14 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t iters, uint32_t seed,
                     uint32_t lo = uint32_t(acc[k]);
                     lo = lo * y + uint32_t(acc[k] >> 32);                                        // IMAD
                     acc[k] = (acc[k] & 0xffffffff00000000ull) | lo;
+                } else if (KIND == 3) {
+                    uint32_t lo = uint32_t(acc[k]);
+                    lo = __umulhi(lo, y) + uint32_t(acc[k] >> 32);                               // IMAD.HI.U32
+                    acc[k] = (acc[k] & 0xffffffff00000000ull) | lo;
+                } else if (KIND == 4) {
+                    uint32_t lo = uint32_t(acc[k]), hi = uint32_t(acc[k] >> 32);
+                    lo = lo + hi + y; hi = hi + lo + y;                                          // 2 x IADD3
+                    acc[k] = (uint64_t(hi) << 32) | lo;
                 } else {
                     uint32_t a = uint32_t(acc[k]), b = uint32_t(acc[k] >> 32);
                     uint32_t r = __funnelshift_r(a, a, 7) ^ (a & b) ^ (~a & y);                 // SHF + LOP3 (+LOP3)
@@ -53,7 +61,7 @@ extern "C" int32_t b200_measure_int_peak(int32_t kind, double* gops) {
     Engine& e = engine();
     std::unique_lock<std::mutex> lk(e.mu);
     if (!e.ready) return B200_ERR_NOT_INITIALIZED;
-    if (!gops || kind < 0 || kind > 2) return B200_ERR_BAD_ARG;
+    if (!gops || kind < 0 || kind > 4) return B200_ERR_BAD_ARG;
     B200_CUDA_TRY(cudaSetDevice(e.device));
     int sms = 0;
     B200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e.device));
@@ -65,7 +73,9 @@ extern "C" int32_t b200_measure_int_peak(int32_t kind, double* gops) {
         B200_CUDA_TRY(cudaEventRecord(e.ev0, e.stream));
         if (kind == 0) k_int_peak<0><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         else if (kind == 1) k_int_peak<1><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
-        else k_int_peak<2><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else if (kind == 2) k_int_peak<2><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else if (kind == 3) k_int_peak<3><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else k_int_peak<4><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         e.launches++;
         B200_CUDA_TRY(cudaEventRecord(e.ev1, e.stream));
         B200_CUDA_TRY(cudaGetLastError());
@@ -75,7 +85,7 @@ extern "C" int32_t b200_measure_int_peak(int32_t kind, double* gops) {
         if (rep > 0 && ms < best) best = ms;
     }
     cudaFree(d);
-    const double ops_per_thread = double(iters) * 32.0 * (kind == 2 ? 4.0 : 1.0);  // kind 2: SHF + 2 LOP3 + IADD3 per step
+    const double ops_per_thread = double(iters) * 32.0 * (kind == 2 ? 4.0 : kind == 4 ? 2.0 : 1.0);  // kind 2: SHF + 2 LOP3 + IADD3 per step; kind 4: 2 IADD3
     *gops = double(blocks) * threads * ops_per_thread / (double(best) * 1e-3) / 1e9;
     return B200_SUCCESS;
 }

@@ -37,9 +37,11 @@ static const fp P = {{0xb9feffffffffaaabull, 0x1eabfffeb153ffffull, 0x6730d2a0f6
                       0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull}};
 static const uint64_t N0 = 0x89f3fffcfffcfffdull; /* -p^-1 mod 2^64 */
 static fp R1, R2;                                  /* 2^384 mod p, 2^768 mod p (computed at init) */
-static uint64_t g_fp_mul_count; /* not thread-safe: read it only around single-threaded calls */
-ORC_EXPORT uint64_t orc_fp_mul_count(void) { return g_fp_mul_count; }
-ORC_EXPORT void orc_fp_mul_count_reset(void) { g_fp_mul_count = 0; }
+/* instrumented Fp-product counter: enabled only between reset() and count(), single-threaded use */
+static uint64_t g_fp_mul_count;
+static int g_count_on;
+ORC_EXPORT uint64_t orc_fp_mul_count(void) { g_count_on = 0; return g_fp_mul_count; }
+ORC_EXPORT void orc_fp_mul_count_reset(void) { g_fp_mul_count = 0; g_count_on = 1; }
 
 static int fp_is_zero(const fp *a) { uint64_t x = 0; for (int i = 0; i < 6; i++) x |= a->l[i]; return x == 0; }
 static int fp_eq(const fp *a, const fp *b) { uint64_t x = 0; for (int i = 0; i < 6; i++) x |= a->l[i] ^ b->l[i]; return x == 0; }
@@ -59,7 +61,7 @@ static void fp_sub(fp *r, const fp *a, const fp *b) { fp t; if (raw_sub(&t, a, b
 static void fp_neg(fp *r, const fp *a) { if (fp_is_zero(a)) *r = *a; else raw_sub(r, &P, a); }
 static void fp_mul(fp *r, const fp *a, const fp *b) {
     uint64_t t[8] = {0};
-    g_fp_mul_count++;
+    if (g_count_on) g_fp_mul_count++;
     for (int i = 0; i < 6; i++) {
         u128 c = 0;
         for (int j = 0; j < 6; j++) { c += (u128)a->l[j] * b->l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
