@@ -12,8 +12,9 @@
 namespace b200 {
 namespace {
 
-__global__ void __launch_bounds__(128) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
-                                                      G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
+                                                                G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t b[48];
@@ -113,8 +114,10 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
     if (!fp_eq(l, r)) bad++;
     fp_sqr(l, a); fp_mul(r, a, a);
     if (!fp_eq(l, r)) bad++;
-    fp_mul_portable(r, a, b);  // tuned PTX product vs the portable one
+    fp_mul_portable(r, a, b);  // tuned PTX product / square vs the portable product
     if (!fp_eq(ab, r)) bad++;
+    fp_mul_portable(r, a, a); fp_sqr(l, a);
+    if (!fp_eq(l, r)) bad++;
     if ((i & 63) == 0 && !fp_is_zero(a)) {
         fp_inv(t, a); fp_mul(t, t, a);
         if (!fp_eq(t, fp_one())) bad++;
@@ -124,9 +127,19 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
 
 }  // namespace
 
+// tuning knob (B200_G1_VARIANT): 0 = 128 threads x 2 CTAs/SM (248 regs, no spills), 1 = 128 x 3 (168 regs),
+// 2 = 64 x 4 (248 regs), 3 = 256 x 1
+static int g_g1_variant = 0;
+void set_g1_variant(int v) { if (v >= 0 && v <= 3) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;
-    k_g1_validate<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(keys, n, out, codes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (g_g1_variant) {
+    case 1: k_g1_validate<128, 3><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
+    case 2: k_g1_validate<64, 4><<<(n + 63) / 64, 64, 0, st>>>(keys, n, out, codes); break;
+    case 3: k_g1_validate<256, 1><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
+    default: k_g1_validate<128, 2><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
+    }
 }
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,
                          uint32_t n_tuples, G1Aff* agg, int32_t* pk_code, uint32_t* flags, uint32_t extra_flags,

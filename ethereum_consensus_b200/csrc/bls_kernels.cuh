@@ -14,6 +14,7 @@ enum : uint32_t { TUPLE_FLAG_EMPTY = 1u, TUPLE_FLAG_AGG_INF = 2u };
 enum : int32_t { SIG_OK = 0, SIG_NOT_IN_GROUP = -1 };  // >0: blst decode error code
 
 // K1: key_validate every 48-byte public key -> affine point + blst code
+void set_g1_variant(int v);
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream);
 // K2: per tuple t, sum the validated keys [off[t], off[t+1]) (or gather through `index` when non-null);
 //     first failing key (in order) decides pk_code[t]

@@ -8,6 +8,7 @@
 //   stream B: H2D sigs,msgs    | K3 sig decompress+subgroup (T) | K4 hash_to_G2 (T) ---------------+ |
 //   stream A: wait(B) | K5 Miller loops (2T threads) | K6 Gt product + final exponentiation (T) | D2H codes
 // Registry mode skips K1: validated affine keys stay resident in HBM and K2 gathers them by validator index.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -31,6 +32,7 @@ struct BlsState {
 static int32_t bls_state(Engine& e, BlsState** out) {
     if (!e.bls) {
         BlsState* s = new BlsState();
+        if (const char* v = getenv("B200_G1_VARIANT")) set_g1_variant(atoi(v));
         B200_CUDA_TRY(cudaStreamCreateWithFlags(&s->sb, cudaStreamNonBlocking));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));

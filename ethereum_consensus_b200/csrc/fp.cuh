@@ -166,7 +166,21 @@ void fp_mul(Fp& r, const Fp& a, const Fp& b) {
     fp_mul_portable(r, a, b);
 #endif
 }
-B200_HD void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
+#if defined(B200_FP_MUL_NOINLINE)
+B200_HD_NOINLINE
+#else
+B200_HD
+#endif
+void fp_sqr(Fp& r, const Fp& a) {
+#if defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE)
+    Fp out;
+    fp_sqr_ptx_core(out.l, a.l);   // dedicated square: 222 wide multiply-adds instead of 288
+    fp_reduce_once(out);
+    r = out;
+#else
+    fp_mul_portable(r, a, a);
+#endif
+}
 
 B200_HD void fp_to_mont(Fp& r, const Fp& a) { const Fp r2 = B200_FP_R2; fp_mul(r, a, r2); }
 B200_HD void fp_from_mont(Fp& r, const Fp& a) {

@@ -166,5 +166,9 @@ extern "C" HM int hm_fp_mul_emul_matches(const uint32_t* a, const uint32_t* b) {
     fp_mul_portable(want, x, y);
     fp_mul_emul_core(got.l, x.l, y.l);
     fp_reduce_once(got);
+    if (!fp_eq(want, got)) return 0;
+    fp_mul_portable(want, x, x);
+    fp_sqr_emul_core(got.l, x.l);
+    fp_reduce_once(got);
     return fp_eq(want, got);
 }
