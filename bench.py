@@ -205,7 +205,7 @@ def main():
     # ---------------------------------------------------------------- our arm
     import torch
     import torch.distributed as dist
-    from ethereum_consensus_b200 import _lib, crypto, ssz, state as S
+    from ethereum_consensus_b200 import _lib, crypto, parallel, ssz, state as S
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -234,13 +234,12 @@ def main():
 
     w = make_bls_workload(orc_bls, T, K, rank, threads=host_threads)
     pks, off, msgs, sigs = pin(w["pks"]), w["off"], pin(w["msgs"]), pin(w["sigs"])
-    gathered = [torch.empty(T, dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
 
     def step():
         codes = crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs)
-        if world > 1:  # the path's one exchange step: every rank learns every shard's verdicts
-            dist.all_gather(gathered, torch.from_numpy(codes).cuda())
-            torch.cuda.synchronize()
+        if world > 1:  # the path's one exchange step: every rank learns every shard's verdicts (NCCL all_gather)
+            everyone = parallel.all_gather_codes(codes)
+            assert len(everyone) == world * T
         return codes
 
     for _ in range(args.warmup):
@@ -371,12 +370,7 @@ def main():
                 flush_l2()
                 barrier()
                 t0 = time.perf_counter()
-                mine = ssz.shard_roots(host, "mainnet", rank, world)
-                tl = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
-                parts = [torch.empty_like(tl) for _ in range(world)]
-                dist.all_gather(parts, tl)
-                allr = b"".join(bytes(p.cpu().numpy()) for p in parts)
-                root = ssz.combine_roots(host, "mainnet", world, allr)
+                root = parallel.sharded_beacon_state_root(host, "mainnet", rank, world)
                 barrier()
                 if i >= 3:
                     es.append(max_over_ranks((time.perf_counter() - t0) * 1e3))

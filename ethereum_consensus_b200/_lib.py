@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libb200_consensus.so"
+LIB_PATH = Path(os.environ.get("B200_LIB", PKG / "libb200_consensus.so"))  # B200_LIB: alternate build for A/B tuning
 
 # return codes (include/b200_consensus.h)
 SUCCESS, BAD_ENCODING, POINT_NOT_ON_CURVE, POINT_NOT_IN_GROUP = 0, 1, 2, 3

@@ -23,7 +23,12 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> Path:
+    """`defines`/`suffix`: alternate tuning build, e.g. build(defines=["B200_FP_SQR_VIA_MUL"], suffix="_sqrmul")."""
+    global LIB, OBJ
+    if suffix:
+        LIB = PKG / f"libb200_consensus{suffix}.so"
+        OBJ = PKG / f"build{suffix}"
     srcs = sorted(CSRC.glob("*.cu"))
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((PKG.parent / "include").glob("*.h"))
     OBJ.mkdir(exist_ok=True)
@@ -35,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def cc(job):
         s, o = job
-        cmd = [NVCC, *FLAGS, "-c", str(s), "-o", str(o)]
+        cmd = [NVCC, *FLAGS, *[f"-D{d}" for d in defines], "-c", str(s), "-o", str(o)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,4 +63,6 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    suf = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, suffix=suf))

@@ -5,6 +5,14 @@
 // k_g1_validate : one thread per key, Fp limbs in registers; 48 B in, 100 B out.  Integer-pipe bound.
 // k_g1_aggregate: one warp per tuple; lanes stride over the tuple's keys with mixed additions, then a
 //                 5-round shared-memory tree of Jacobian additions; lane 0 normalises to affine.
+// measured on B200 (profiles/r1_tuning.md): in this kernel the dedicated square's extra carry bookkeeping cancels its
+// 23 % fewer wide MADs, and inlined products beat by-value calls -> squares use the product, everything inlined.
+#ifndef B200_G1_PTX_SQR
+#define B200_FP_SQR_VIA_MUL 1
+#endif
+#if defined(B200_G1_CALL_MUL)  // A/B knob: by-value function calls instead of inlined products in the per-key kernel
+#define B200_FP_MUL_CALL 1
+#endif
 #include <cuda_runtime.h>
 
 #include "bls_kernels.cuh"
@@ -127,18 +135,18 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
 
 }  // namespace
 
-// tuning knob (B200_G1_VARIANT): 0 = 128 threads x 2 CTAs/SM (248 regs, no spills), 1 = 128 x 3 (168 regs),
-// 2 = 64 x 4 (248 regs), 3 = 256 x 1
+// tuning knob (B200_G1_VARIANT): threads x min CTAs/SM = 0: 256x1, 1: 128x2, 2: 128x3, 3: 256x2, 4: 128x4
 static int g_g1_variant = 0;
-void set_g1_variant(int v) { if (v >= 0 && v <= 3) g_g1_variant = v; }
+void set_g1_variant(int v) { if (v >= 0 && v <= 4) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (g_g1_variant) {
-    case 1: k_g1_validate<128, 3><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
-    case 2: k_g1_validate<64, 4><<<(n + 63) / 64, 64, 0, st>>>(keys, n, out, codes); break;
-    case 3: k_g1_validate<256, 1><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
-    default: k_g1_validate<128, 2><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
+    case 1: k_g1_validate<128, 2><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
+    case 2: k_g1_validate<128, 3><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
+    case 3: k_g1_validate<256, 2><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
+    case 4: k_g1_validate<128, 4><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
+    default: k_g1_validate<256, 1><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
     }
 }
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,

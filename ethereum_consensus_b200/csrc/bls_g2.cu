@@ -2,7 +2,7 @@
 // `sig_groupcheck = true` of /root/reference/ethereum-consensus/src/crypto/bls.rs:71,106,126) and hash_to_G2 of
 // the signing roots.  One thread per signature / message; these kernels see only T (thousands) of items, so
 // they run concurrently with the wide G1 kernels on a second stream.
-#define B200_FP_MUL_NOINLINE 1
+#define B200_FP_MUL_CALL 1
 #define B200_FP2_NOINLINE 1
 #define B200_TOWER_NOINLINE 1
 #include <cuda_runtime.h>

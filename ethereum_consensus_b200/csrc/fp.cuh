@@ -149,38 +149,53 @@ B200_HD void fp_mul_portable(Fp& r, const Fp& a, const Fp& b) {
 #include "fp_mul_ptx.cuh"
 namespace b200 {
 
-// The product used everywhere: on the device the generated inline-PTX sequence (mad.lo.cc/madc.hi.cc pairs that
+// The product used everywhere: on the device the generated inline-PTX sequences (mad.lo.cc/madc.hi.cc pairs that
 // ptxas fuses into IMAD.WIDE.U32.X carry chains, inputs must be < p); on the host the portable code above.
-#if defined(B200_FP_MUL_NOINLINE)
-B200_HD_NOINLINE
-#else
-B200_HD
-#endif
-void fp_mul(Fp& r, const Fp& a, const Fp& b) {
+// B200_FP_MUL_CALL: emit them as real functions taking/returning Fp BY VALUE — the ABI keeps all 36 limbs in
+// registers (0-byte stack frame), so a call costs ~40 register moves but every warp of the kernel shares one ~13 KB
+// instruction footprint instead of hundreds of inlined copies (the per-key kernel was instruction-fetch limited).
 #if defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE)
+#if defined(B200_FP_MUL_CALL)
+static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) {
+    Fp out;
+    fp_mul_ptx_core(out.l, a.l, b.l);
+    fp_reduce_once(out);
+    return out;
+}
+static __device__ __noinline__ Fp fp_sqr_call(Fp a) {
+    Fp out;
+#if defined(B200_FP_SQR_VIA_MUL)
+    fp_mul_ptx_core(out.l, a.l, a.l);
+#else
+    fp_sqr_ptx_core(out.l, a.l);   // dedicated square: 222 wide multiply-adds instead of 288
+#endif
+    fp_reduce_once(out);
+    return out;
+}
+B200_HD void fp_mul(Fp& r, const Fp& a, const Fp& b) { r = fp_mul_call(a, b); }
+B200_HD void fp_sqr(Fp& r, const Fp& a) { r = fp_sqr_call(a); }
+#else
+B200_HD void fp_mul(Fp& r, const Fp& a, const Fp& b) {
     Fp out;
     fp_mul_ptx_core(out.l, a.l, b.l);
     fp_reduce_once(out);
     r = out;
-#else
-    fp_mul_portable(r, a, b);
-#endif
 }
-#if defined(B200_FP_MUL_NOINLINE)
-B200_HD_NOINLINE
-#else
-B200_HD
-#endif
-void fp_sqr(Fp& r, const Fp& a) {
-#if defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE)
+B200_HD void fp_sqr(Fp& r, const Fp& a) {
     Fp out;
-    fp_sqr_ptx_core(out.l, a.l);   // dedicated square: 222 wide multiply-adds instead of 288
+#if defined(B200_FP_SQR_VIA_MUL)
+    fp_mul_ptx_core(out.l, a.l, a.l);
+#else
+    fp_sqr_ptx_core(out.l, a.l);
+#endif
     fp_reduce_once(out);
     r = out;
-#else
-    fp_mul_portable(r, a, a);
-#endif
 }
+#endif
+#else
+B200_HD void fp_mul(Fp& r, const Fp& a, const Fp& b) { fp_mul_portable(r, a, b); }
+B200_HD void fp_sqr(Fp& r, const Fp& a) { fp_mul_portable(r, a, a); }
+#endif
 
 B200_HD void fp_to_mont(Fp& r, const Fp& a) { const Fp r2 = B200_FP_R2; fp_mul(r, a, r2); }
 B200_HD void fp_from_mont(Fp& r, const Fp& a) {

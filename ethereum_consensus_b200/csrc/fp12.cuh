@@ -130,6 +130,36 @@ B200_BIG void fp12_inv(Fp12& r, const Fp12& a) {
     fp6_neg(r.c1, t1);
 }
 
+// Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of the final
+// exponentiation): three Fp4 squarings = 9 Fp2 squarings instead of 12 Fp2 products.
+B200_HD void fp4_sqr(Fp2& c0, Fp2& c1, const Fp2& a, const Fp2& b) {
+    Fp2 t0, t1, t2;
+    fp2_sqr(t0, a);
+    fp2_sqr(t1, b);
+    fp2_mul_xi(t2, t1);
+    fp2_add(c0, t2, t0);
+    fp2_add(t2, a, b);
+    fp2_sqr(t2, t2);
+    fp2_sub(t2, t2, t0);
+    fp2_sub(c1, t2, t1);
+}
+B200_BIG void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
+    Fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+    Fp2 t0, t1, t2, t3;
+    fp4_sqr(t0, t1, z0, z1);
+    fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
+    fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
+    fp4_sqr(t0, t1, z2, z3);
+    fp4_sqr(t2, t3, z4, z5);
+    fp2_sub(z4, t0, z4); fp2_dbl(z4, z4); fp2_add(z4, z4, t0);
+    fp2_add(z5, t1, z5); fp2_dbl(z5, z5); fp2_add(z5, z5, t1);
+    fp2_mul_xi(t0, t3);
+    fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
+    fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
+    r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
+    r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
+}
+
 // frobenius^k, k in {1,2,3}: coefficient at w^i -> conj^k(coefficient) * xi^(i (p^k - 1)/6)
 template <int K> B200_HD Fp2 frob_gamma(int i);
 #define B200_DEF_GAMMA(K)                                                             \

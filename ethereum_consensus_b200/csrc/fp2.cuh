@@ -84,26 +84,55 @@ B200_BIG void fp2_pow(Fp2& r, const Fp2& a, const uint32_t* e) {
     }
     r = acc;
 }
-// Square root for p = 3 (mod 4) (Adj & Rodriguez-Henriquez, Alg. 9); returns false if `a` is a non-residue.
+// halve in Fp (Montgomery form is linear): (a + (a odd ? p : 0)) >> 1
+B200_HD void fp_half(Fp& r, const Fp& a) {
+    const Fp p = fp_p();
+    Fp t = a;
+    uint32_t carry = 0;
+    if (a.l[0] & 1) carry = fp_add_raw(t, a, p);
+#pragma unroll
+    for (int i = 0; i < 11; i++) t.l[i] = (t.l[i] >> 1) | (t.l[i + 1] << 31);
+    t.l[11] = (t.l[11] >> 1) | (carry << 31);
+    r = t;
+}
+// For d != 0 in Fp: one exponentiation t = d^((p-3)/4) gives both candidates: x = d*t (the square root if d is a
+// residue) and t = 1/x.  Returns whether d is a quadratic residue.
+B200_HD bool fp_sqrt_and_inv(Fp& x, Fp& xinv, const Fp& d) {
+    Fp t, chk;
+    fp_pow(t, d, B200_EXP_TABLE(exp_p_minus_3_div_4));
+    fp_mul(x, d, t);
+    fp_sqr(chk, x);
+    xinv = t;
+    return fp_eq(chk, d);
+}
+// Square root in Fp2 by the complex method (norm to Fp, two Fp exponentiations instead of two Fp2 ones);
+// returns false if `a` is not a square.  Either root may be returned: callers fix the sign (sgn0 / flag bit).
 B200_BIG bool fp2_sqrt(Fp2& r, const Fp2& a) {
     if (fp2_is_zero(a)) { r = a; return true; }
-    Fp2 a1, alpha, x0, x, chk;
-    fp2_pow(a1, a, B200_EXP_TABLE(exp_p_minus_3_div_4));
-    fp2_sqr(alpha, a1);
-    fp2_mul(alpha, alpha, a);
-    fp2_mul(x0, a1, a);
-    Fp2 minus_one;
-    fp_neg(minus_one.c0, fp_one());
-    minus_one.c1 = fp_zero();
-    if (fp2_eq(alpha, minus_one)) {
-        fp_neg(x.c0, x0.c1);  // u * x0
-        x.c1 = x0.c0;
+    Fp2 x;
+    if (fp_is_zero(a.c1)) {
+        Fp s;
+        if (fp_sqrt(s, a.c0)) { x.c0 = s; x.c1 = fp_zero(); }
+        else { Fp n; fp_neg(n, a.c0); fp_sqrt(s, n); x.c0 = fp_zero(); x.c1 = s; }  // (s u)^2 = -s^2 = a0
     } else {
-        Fp2 b, one = fp2_one();
-        fp2_add(b, one, alpha);
-        fp2_pow(b, b, B200_EXP_TABLE(exp_p_minus_1_div_2));
-        fp2_mul(x, b, x0);
+        Fp n, t, s, d, x0, x0inv;
+        fp_sqr(n, a.c0);
+        fp_sqr(t, a.c1);
+        fp_add(n, n, t);                       // norm
+        if (!fp_sqrt(s, n)) return false;      // a square in Fp2 has a square norm
+        fp_add(d, a.c0, s);
+        fp_half(d, d);                         // (a0 + s)/2
+        bool ok = !fp_is_zero(d) && fp_sqrt_and_inv(x0, x0inv, d);
+        if (!ok) {
+            fp_sub(d, a.c0, s);
+            fp_half(d, d);                     // (a0 - s)/2
+            if (fp_is_zero(d) || !fp_sqrt_and_inv(x0, x0inv, d)) return false;
+        }
+        fp_mul(t, a.c1, x0inv);
+        fp_half(t, t);                         // x1 = a1 / (2 x0)
+        x.c0 = x0; x.c1 = t;
     }
+    Fp2 chk;
     fp2_sqr(chk, x);
     r = x;
     return fp2_eq(chk, a);

@@ -84,13 +84,13 @@ B200_BIG void miller_loop(Fp12& f, const G1Aff& p, const G2Aff& q) {
     fp12_conj(f, f);  // z < 0
 }
 
-// g^|z| by square-and-multiply
+// g^|z| by square-and-multiply; g must lie in the cyclotomic subgroup (true after the easy part)
 B200_BIG void fp12_pow_z(Fp12& r, const Fp12& g) {
     Fp12 acc = g;
     const uint64_t z = B200_Z_ABS;
 #pragma unroll 1
     for (int bit = 62; bit >= 0; bit--) {
-        fp12_sqr(acc, acc);
+        fp12_cyclotomic_sqr(acc, acc);
         if ((z >> bit) & 1) fp12_mul(acc, acc, g);
     }
     r = acc;

@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(kFinisherThreads) k_merkle_finisher(uint32_t* 
 }  // namespace
 
 // occupancy knobs (registers per thread vs resident warps); set once from B200_SSZ_MINB_{VALIDATORS,STAGE}
-int g_minb_validators = 3;
-int g_minb_stage = 3;
+int g_minb_validators = 4;
+int g_minb_stage = 4;
 void set_ssz_tuning(int minb_validators, int minb_stage) {
     if (minb_validators >= 2 && minb_validators <= 4) g_minb_validators = minb_validators;
     if (minb_stage >= 2 && minb_stage <= 4) g_minb_stage = minb_stage;

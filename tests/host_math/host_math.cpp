@@ -126,6 +126,11 @@ HM int hm_fp12_selftest(void) {
     { Fp12 d; fp12_inv(d, c); fp12_mul(d, d, b); if (fp12_is_one(d)) ok |= 8; }
     fp12_frobenius<1>(b, c); fp12_frobenius<3>(c, a);
     { Fp12 d; fp12_inv(d, c); fp12_mul(d, d, b); if (fp12_is_one(d)) ok |= 16; }
+    // cyclotomic squaring == generic squaring on the cyclotomic subgroup (after the easy part)
+    { Fp12 e, t0, t1, s1, s2;
+      fp12_inv(t0, a); fp12_conj(t1, a); fp12_mul(t0, t1, t0); fp12_frobenius<2>(t1, t0); fp12_mul(e, t1, t0);
+      fp12_sqr(s1, e); fp12_cyclotomic_sqr(s2, e);
+      fp12_inv(t0, s1); fp12_mul(t0, t0, s2); if (fp12_is_one(t0)) ok |= 32; }
     return ok;
 }
 

@@ -88,7 +88,7 @@ def test_host_math_fields_match_oracle(host_math):
         host_math.hm_fp2_op(2, enc(a), enc(b), out); assert dec(out) == bo.f2_inv(a)
         ok = host_math.hm_fp2_op(3, enc(a), enc(b), out); assert bool(ok) == (bo.f2_sqrt(a) is not None)
         assert host_math.hm_fp2_op(4, enc(a), enc(b), out) == bo.f2_sgn0(a)
-    assert host_math.hm_fp12_selftest() == 31
+    assert host_math.hm_fp12_selftest() == 63
 
 
 def test_host_math_hash_to_g2_matches_oracle(host_math):
