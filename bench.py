@@ -38,7 +38,10 @@ SIG_NOT_IN_GROUP = None  # filled from tests/golden/bls_cases.json
 
 # ------------------------------------------------------------------------------------------------ helpers
 def load_oracles():
-    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
+    import fcntl
+    with open(ROOT / "oracle" / ".build.lock", "w") as lk:  # ranks of one node must not rebuild the .so concurrently
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
     bls = C.CDLL(str(ROOT / "oracle" / "liboracle_bls.so"))
     ssz = C.CDLL(str(ROOT / "oracle" / "liboracle_ssz.so"))
     vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
@@ -208,6 +211,7 @@ def main():
     from ethereum_consensus_b200 import _lib, crypto, parallel, ssz, state as S
 
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.init(local_rank)
