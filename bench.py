@@ -211,7 +211,8 @@ def main():
     from ethereum_consensus_b200 import _lib, crypto, parallel, ssz, state as S
 
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.init(local_rank)
