@@ -163,6 +163,13 @@ def main():
     ap.add_argument("--validators", type=int, default=1 << 20)
     ap.add_argument("--skip-ssz", action="store_true")
     args = ap.parse_args()
+    # Libraries (NCCL's version banner, make, ...) may write to fd 1; the contract is ONE JSON line on stdout from rank 0.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -202,7 +209,7 @@ def main():
                      "cpu_baseline": {"value": v, "unit": "tuples/s", "cores": host_threads, "kind": "port",
                                       "sample": f"{sample} of the {T} tuples per step, all host threads (plain-C restatement, not blst)"},
                      "e2e": {"value": v, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---------------------------------------------------------------- our arm
@@ -403,7 +410,7 @@ def main():
                            "cpu_baseline": {"ms_1_thread": cpu1, f"ms_{host_threads}_threads": cpun, "kind": "port",
                                             "note": "plain-C restatement with SHA-NI when the host has it (not ssz_rs)"}}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
