@@ -1,0 +1,97 @@
+"""Deferred signature-set verification for one block: the collector that turns the
+signature checks `process_block` performs one at a time into ONE batch call, then replays the per-tuple verdicts in
+execution order so the observable behaviour is the reference's:
+
+* the first failing check aborts with that check's error,
+* except deposits, whose invalid signatures are skipped silently
+  (/root/reference/ethereum-consensus/src/phase0/block_processing.rs:389-392),
+* `is_valid_indexed_attestation`'s host-side checks (non-empty, sorted, unique, index in range) run before any
+  signature work and fail first (/root/reference/ethereum-consensus/src/phase0/helpers.rs:94-131).
+
+Sites, in the order of deneb `process_block` (deneb/block_processing.rs:402-408, spec/mod.rs:219-230):
+block proposer, randao, proposer slashings, attester slashings, attestations, deposits, voluntary exits,
+bls-to-execution changes, sync aggregate.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import crypto
+
+SITES = ("block_signature", "randao", "proposer_slashing", "attester_slashing", "attestation", "deposit", "voluntary_exit",
+         "bls_to_execution_change", "sync_aggregate")
+
+
+class InvalidIndexedAttestation(ValueError):
+    """AttestingIndicesEmpty / AttestingIndicesNotSorted / DuplicateIndices / InvalidIndex (phase0/helpers.rs:94-131)."""
+
+
+@dataclass
+class _Entry:
+    site: str
+    pubkeys: List[bytes]
+    signing_root: bytes
+    signature: bytes
+    tolerant: bool = False
+    eth_variant: bool = False  # eth_fast_aggregate_verify semantics (sync aggregate)
+
+
+@dataclass
+class SignatureSet:
+    entries: List[_Entry] = field(default_factory=list)
+
+    def add(self, site: str, pubkeys: Sequence[bytes], signing_root: bytes, signature: bytes, tolerant: bool = False,
+            eth_variant: bool = False) -> None:
+        assert site in SITES and len(signing_root) == 32
+        self.entries.append(_Entry(site, [bytes(p) for p in pubkeys], bytes(signing_root), bytes(signature), tolerant, eth_variant))
+
+    def add_indexed_attestation(self, site: str, validator_pubkeys, attesting_indices: Sequence[int], signing_root: bytes,
+                                signature: bytes) -> None:
+        """`is_valid_indexed_attestation` up to the BLS call (phase0/helpers.rs:94-131)."""
+        idx = list(attesting_indices)
+        if not idx:
+            raise InvalidIndexedAttestation("AttestingIndicesEmpty")
+        dup = set()
+        for prev, cur in zip(idx, idx[1:]):
+            if cur < prev:
+                raise InvalidIndexedAttestation("AttestingIndicesNotSorted")
+            if cur == prev:
+                dup.add(cur)
+        if dup:
+            raise InvalidIndexedAttestation(f"DuplicateIndices({sorted(dup)})")
+        n = len(validator_pubkeys)
+        for i in idx:
+            if i >= n:
+                raise InvalidIndexedAttestation(f"InvalidIndex({i})")
+        self.add(site, [validator_pubkeys[i] for i in idx], signing_root, signature)
+
+    # ---- one batch call for the whole block
+    def verify(self) -> np.ndarray:
+        """int32 code per entry, exactly what the per-call reference functions would have returned."""
+        t = len(self.entries)
+        if t == 0:
+            return np.zeros(0, dtype=np.int32)
+        pks = np.frombuffer(b"".join(p for e in self.entries for p in e.pubkeys) or b"", dtype=np.uint8)
+        off = np.cumsum([0] + [len(e.pubkeys) for e in self.entries]).astype(np.uint32)
+        msgs = np.frombuffer(b"".join(e.signing_root for e in self.entries), dtype=np.uint8)
+        sigs = np.frombuffer(b"".join(e.signature for e in self.entries), dtype=np.uint8)
+        codes = crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs).copy()
+        for i, e in enumerate(self.entries):  # eth_fast_aggregate_verify: no participants + infinity signature is Ok
+            if e.eth_variant and not e.pubkeys and e.signature == crypto.INFINITY_COMPRESSED_SIGNATURE:
+                codes[i] = 0
+        return codes
+
+    def first_failure(self, codes: Optional[np.ndarray] = None):
+        """(index, site, code) of the first check that aborts the block, or None; tolerant entries never abort."""
+        if codes is None:
+            codes = self.verify()
+        for i, (e, c) in enumerate(zip(self.entries, codes)):
+            if c != 0 and not e.tolerant:
+                return i, e.site, int(c)
+        return None
+
+    def skipped_deposits(self, codes: np.ndarray) -> List[int]:
+        return [i for i, (e, c) in enumerate(zip(self.entries, codes)) if e.tolerant and c != 0]
