@@ -33,6 +33,13 @@ void launch_miller(const G1Aff* g1, const uint32_t* g1_idx, const G2Aff* g2, con
 // K6: per tuple: merge codes with the reference's precedence, multiply its Miller values, final exponentiation
 void launch_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_code, const uint32_t* flags,
                   const int32_t* sig_code, uint32_t n_tuples, int32_t* out_codes, void* stream);
+// lane-parallel (team) versions of K5 / K6 for tuples with exactly two pairs (bls_vm.cu); vm_init returns 0 on success
+int vm_init(void* stream);
+void launch_vm_miller(const G1Aff* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
+                      const uint32_t* pair_tuple, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,
+                      uint32_t n_pairs, Fp12* f, void* stream);
+void launch_vm_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_code, const uint32_t* flags,
+                     const int32_t* sig_code, uint32_t n_tuples, int32_t* out_codes, void* stream);
 // aggregation helpers for `aggregate` / `eth_aggregate_public_keys`
 void launch_g2_sum_compress(const G2Aff* sigs, const int32_t* sig_code, uint32_t n, uint8_t* out96, int32_t* out_code, void* stream);
 void launch_g1_compress(const G1Aff* p, uint8_t* out48, void* stream);

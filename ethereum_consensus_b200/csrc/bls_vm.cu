@@ -1,0 +1,159 @@
+// Lane-parallel pairing kernels: a TEAM of kVmTeam lanes per (G1, G2) pair / per tuple replays the statically
+// scheduled Fp2 programs of tools/gen_pairing_vm.py (Miller loop, final exponentiation) on a shared-memory register
+// file.  Replaces the one-thread-per-pair kernels of bls_pairing.cu on the batch path: those expose only 2T threads
+// (a ~40 ms latency floor at T = 4096); here 16x more lanes work on the same tuples, products stay inlined PTX.
+#include <cuda_runtime.h>
+
+#include "bls_kernels.cuh"
+#include "pairing_vm.cuh"
+
+namespace b200 {
+namespace {
+
+__global__ void k_vm_consts(const uint32_t* __restrict__ plain, Fp2* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i < kVmConsts) {
+        uint32_t l[24];
+        for (int k = 0; k < 24; k++) l[k] = plain[i * 24 + k];
+        Fp2 v;
+        vm_const_to_mont(v, l);
+        out[i] = v;
+    }
+}
+
+__device__ __forceinline__ void vm_run(const uint32_t* __restrict__ code, int n_rounds, const Fp2* __restrict__ consts,
+                                       const VmRfStrided& rf, uint32_t lane, bool active) {
+#pragma unroll 1
+    for (int r = 0; r < n_rounds; r++) {
+        const uint32_t w = __ldg(code + r * kVmTeam + lane);
+        if (active && (w & 0xffu) != VM_NOP) {
+            Fp2 res;
+            vm_exec(w, rf, consts, res);
+            rf.store((w >> 8) & 0xffu, res);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ bool tuple_dead(uint32_t t, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code) {
+    return pk_code[t] != BLS_SUCCESS || flags[t] != 0 || sig_code[t] != SIG_OK;
+}
+
+// one team per pair
+__global__ void __launch_bounds__(128) k_vm_miller(const uint32_t* __restrict__ code, const Fp2* __restrict__ consts,
+                                                    const G1Aff* __restrict__ g1, const uint32_t* __restrict__ g1_idx,
+                                                    const G2Aff* __restrict__ g2, const uint32_t* __restrict__ g2_idx,
+                                                    const uint32_t* __restrict__ pair_tuple, const int32_t* __restrict__ pk_code,
+                                                    const uint32_t* __restrict__ flags, const int32_t* __restrict__ sig_code,
+                                                    uint32_t n_pairs, Fp12* __restrict__ f) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t team_in_block = threadIdx.x / kVmTeam, lane = threadIdx.x % kVmTeam;
+    const uint32_t i = blockIdx.x * (blockDim.x / kVmTeam) + team_in_block;
+    VmRfStrided rf{smem + team_in_block * (kMillerSlots * kVmSlotWords)};
+    bool active = i < n_pairs && !tuple_dead(pair_tuple[i], pk_code, flags, sig_code);
+    bool trivial = false;  // a point at infinity: the pair contributes 1
+    if (active) {
+        const G1Aff* p = g1 + g1_idx[i];
+        const G2Aff* q = g2 + g2_idx[i];
+        trivial = p->inf || q->inf;
+        if (!trivial) {
+            if (lane == 0) { Fp2 v; v.c0 = p->x; v.c1 = fp_zero(); rf.store(0, v); }
+            if (lane == 1) { Fp2 v; v.c0 = p->y; v.c1 = fp_zero(); rf.store(1, v); }
+            if (lane == 2) rf.store(2, q->x);
+            if (lane == 3) rf.store(3, q->y);
+        }
+    }
+    __syncwarp();
+    vm_run(code, kMillerRounds, consts, rf, lane, active && !trivial);
+    if (active && lane < 6) {
+        // w-power order of the program outputs -> tower slots c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2
+        Fp2 v;
+        if (trivial) v = (lane == 0) ? fp2_one() : fp2_zero();
+        else { const int outs[6] = {kMillerOut[0], kMillerOut[1], kMillerOut[2], kMillerOut[3], kMillerOut[4], kMillerOut[5]}; v = rf.load(uint32_t(outs[lane])); }
+        Fp2* dst = reinterpret_cast<Fp2*>(f + i);
+        const int tower_pos[6] = {0, 3, 1, 4, 2, 5};  // Fp12 memory order: c0.{c0,c1,c2}, c1.{c0,c1,c2}
+        dst[tower_pos[lane]] = v;
+    }
+}
+
+// one team per tuple (two Miller values per tuple: pairs pair_off[t], pair_off[t]+1)
+__global__ void __launch_bounds__(64) k_vm_final(const uint32_t* __restrict__ code, const Fp2* __restrict__ consts,
+                                                  const Fp12* __restrict__ f, const uint32_t* __restrict__ pair_off,
+                                                  const int32_t* __restrict__ pk_code, const uint32_t* __restrict__ flags,
+                                                  const int32_t* __restrict__ sig_code, uint32_t n_tuples,
+                                                  int32_t* __restrict__ out_codes) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t team_in_block = threadIdx.x / kVmTeam, lane = threadIdx.x % kVmTeam;
+    const uint32_t t = blockIdx.x * (blockDim.x / kVmTeam) + team_in_block;
+    VmRfStrided rf{smem + team_in_block * (kFinalSlots * kVmSlotWords)};
+    int32_t code_out = BLS_SUCCESS;
+    bool active = false;
+    if (t < n_tuples) {
+        if (pk_code[t] != BLS_SUCCESS) code_out = pk_code[t];
+        else if (sig_code[t] > 0) code_out = sig_code[t];
+        else if (flags[t] != 0 || sig_code[t] == SIG_NOT_IN_GROUP) code_out = BLS_VERIFY_FAIL;
+        else active = true;
+    }
+    if (active && lane < 12) {
+        const Fp2* src = reinterpret_cast<const Fp2*>(f + pair_off[t] + lane / 6);
+        const int tower_pos[6] = {0, 3, 1, 4, 2, 5};
+        rf.store(lane, src[tower_pos[lane % 6]]);
+    }
+    __syncwarp();
+    vm_run(code, kFinalRounds, consts, rf, lane, active);
+    if (t < n_tuples && lane == 0) {
+        if (active) {
+            const int outs[6] = {kFinalOut[0], kFinalOut[1], kFinalOut[2], kFinalOut[3], kFinalOut[4], kFinalOut[5]};
+            bool one = fp2_eq(rf.load(uint32_t(outs[0])), fp2_one());
+#pragma unroll 1
+            for (int k = 1; k < 6; k++) one = one && fp2_is_zero(rf.load(uint32_t(outs[k])));
+            code_out = one ? BLS_SUCCESS : BLS_VERIFY_FAIL;
+        }
+        out_codes[t] = code_out;
+    }
+}
+
+}  // namespace
+
+static uint32_t* g_d_miller_code = nullptr;
+static uint32_t* g_d_final_code = nullptr;
+static Fp2* g_d_consts = nullptr;
+
+int vm_init(void* stream) {
+    if (g_d_consts) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t* d_plain = nullptr;
+    if (cudaMalloc(&g_d_miller_code, sizeof(h_miller_code)) != cudaSuccess) return 1;
+    if (cudaMalloc(&g_d_final_code, sizeof(h_final_code)) != cudaSuccess) return 1;
+    if (cudaMalloc(&g_d_consts, sizeof(Fp2) * kVmConsts) != cudaSuccess) return 1;
+    if (cudaMalloc(&d_plain, sizeof(h_vm_consts)) != cudaSuccess) return 1;
+    cudaMemcpyAsync(g_d_miller_code, h_miller_code, sizeof(h_miller_code), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(g_d_final_code, h_final_code, sizeof(h_final_code), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_plain, h_vm_consts, sizeof(h_vm_consts), cudaMemcpyHostToDevice, st);
+    k_vm_consts<<<1, 32, 0, st>>>(d_plain, g_d_consts);
+    cudaFuncSetAttribute(k_vm_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kMillerSlots * kVmSlotWords * 4);
+    cudaFuncSetAttribute(k_vm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kFinalSlots * kVmSlotWords * 4);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    cudaFree(d_plain);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+void launch_vm_miller(const G1Aff* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
+                      const uint32_t* pair_tuple, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,
+                      uint32_t n_pairs, Fp12* f, void* stream) {
+    if (!n_pairs) return;
+    const int threads = 128, teams = threads / kVmTeam;
+    const size_t smem = size_t(teams) * kMillerSlots * kVmSlotWords * 4;
+    k_vm_miller<<<(n_pairs + teams - 1) / teams, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+        g_d_miller_code, g_d_consts, g1, g1_idx, g2, g2_idx, pair_tuple, pk_code, flags, sig_code, n_pairs, f);
+}
+void launch_vm_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_code, const uint32_t* flags,
+                     const int32_t* sig_code, uint32_t n_tuples, int32_t* out_codes, void* stream) {
+    if (!n_tuples) return;
+    const int threads = 64, teams = threads / kVmTeam;
+    const size_t smem = size_t(teams) * kFinalSlots * kVmSlotWords * 4;
+    k_vm_final<<<(n_tuples + teams - 1) / teams, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+        g_d_final_code, g_d_consts, f, pair_off, pk_code, flags, sig_code, n_tuples, out_codes);
+}
+
+}  // namespace b200

@@ -27,12 +27,14 @@ struct BlsState {
     DevBuf reg_aff, reg_code;
     size_t reg_n = 0;
     float last_dominant_ms = 0.f;
+    bool use_vm = true;  // lane-parallel pairing kernels (B200_PAIRING_VM=0 selects the one-thread-per-pair kernels)
 };
 
 static int32_t bls_state(Engine& e, BlsState** out) {
     if (!e.bls) {
         BlsState* s = new BlsState();
         if (const char* v = getenv("B200_G1_VARIANT")) set_g1_variant(atoi(v));
+        if (const char* v = getenv("B200_PAIRING_VM")) s->use_vm = atoi(v) != 0;
         B200_CUDA_TRY(cudaStreamCreateWithFlags(&s->sb, cudaStreamNonBlocking));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
@@ -42,6 +44,8 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         B200_CUDA_TRY(cudaEventCreate(&s->ev_d1));
         B200_CUDA_TRY(cudaMalloc(&s->d_negg1, sizeof(G1Aff)));
         launch_neg_g1(s->d_negg1, e.stream);
+        e.launches++;
+        if (vm_init(e.stream) != 0) { e.last_error = "pairing VM initialisation failed"; return B200_ERR_CUDA; }
         e.launches++;
         B200_CUDA_TRY(cudaGetLastError());
         B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
@@ -174,12 +178,25 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     }
     // ---- join, pairing
     B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_b, 0));
-    launch_miller(pair_g1, d_small + o_g1i, d_g2, d_small + o_g1i + n_pairs, d_small + o_g1i + 2 * size_t(n_pairs),
-                  static_cast<const int32_t*>(s.pk_code.p), static_cast<const uint32_t*>(s.flags.p),
-                  static_cast<const int32_t*>(s.sig_code.p), n_pairs, static_cast<Fp12*>(s.f.p), sa);
-    launch_final(static_cast<const Fp12*>(s.f.p), d_small + o_g1i + 3 * size_t(n_pairs), static_cast<const int32_t*>(s.pk_code.p),
-                 static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), T,
-                 static_cast<int32_t*>(s.out.p), sa);
+    const uint32_t* d_g1i = d_small + o_g1i;
+    const uint32_t* d_g2i = d_g1i + n_pairs;
+    const uint32_t* d_ptu = d_g2i + n_pairs;
+    const uint32_t* d_poff = d_ptu + n_pairs;
+    if (mode == MODE_FAST_AGGREGATE && s.use_vm) {
+        launch_vm_miller(pair_g1, d_g1i, d_g2, d_g2i, d_ptu, static_cast<const int32_t*>(s.pk_code.p),
+                         static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), n_pairs,
+                         static_cast<Fp12*>(s.f.p), sa);
+        launch_vm_final(static_cast<const Fp12*>(s.f.p), d_poff, static_cast<const int32_t*>(s.pk_code.p),
+                        static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), T,
+                        static_cast<int32_t*>(s.out.p), sa);
+    } else {
+        launch_miller(pair_g1, d_g1i, d_g2, d_g2i, d_ptu, static_cast<const int32_t*>(s.pk_code.p),
+                      static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), n_pairs,
+                      static_cast<Fp12*>(s.f.p), sa);
+        launch_final(static_cast<const Fp12*>(s.f.p), d_poff, static_cast<const int32_t*>(s.pk_code.p),
+                     static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), T,
+                     static_cast<int32_t*>(s.out.p), sa);
+    }
     e.launches += (n_pairs ? 1 : 0) + (T ? 1 : 0);
     B200_CUDA_TRY(cudaEventRecord(s.ev_k1, sa));
     B200_CUDA_TRY(cudaGetLastError());

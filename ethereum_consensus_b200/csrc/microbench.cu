@@ -32,6 +32,19 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t iters, uint32_t seed,
                     uint32_t lo = uint32_t(acc[k]);
                     lo = __umulhi(lo, y) + uint32_t(acc[k] >> 32);                               // IMAD.HI.U32
                     acc[k] = (acc[k] & 0xffffffff00000000ull) | lo;
+                } else if (KIND == 5) {
+                    // one 52x52->104-bit product by the sampled-FMA trick + integer accumulation of both halves
+                    const double C1 = 20282409603651670423947251286016.0;            // 2^104
+                    const double C2 = 20282409603651670423947251286016.0 + 4503599627370496.0;  // 2^104 + 2^52
+                    double x = __longlong_as_double((acc[k] & 0x000fffffffffffffull) | 0x4330000000000000ull) - 4503599627370496.0;
+                    double yd = double(y);
+                    double hi = __fma_rz(x, yd, C1);
+                    double lo = __fma_rz(x, yd, C2 - hi);
+                    acc[k] += uint64_t(__double_as_longlong(hi)) + uint64_t(__double_as_longlong(lo));
+                } else if (KIND == 6) {
+                    double x = __longlong_as_double(acc[k] | 0x3ff0000000000000ull);
+                    x = __fma_rz(x, 1.0000001, 0.5);                                              // DFMA
+                    acc[k] = uint64_t(__double_as_longlong(x)) & 0x000fffffffffffffull;
                 } else if (KIND == 4) {
                     uint32_t lo = uint32_t(acc[k]), hi = uint32_t(acc[k] >> 32);
                     lo = lo + hi + y; hi = hi + lo + y;                                          // 2 x IADD3
@@ -61,7 +74,7 @@ extern "C" int32_t b200_measure_int_peak(int32_t kind, double* gops) {
     Engine& e = engine();
     std::unique_lock<std::mutex> lk(e.mu);
     if (!e.ready) return B200_ERR_NOT_INITIALIZED;
-    if (!gops || kind < 0 || kind > 4) return B200_ERR_BAD_ARG;
+    if (!gops || kind < 0 || kind > 6) return B200_ERR_BAD_ARG;
     B200_CUDA_TRY(cudaSetDevice(e.device));
     int sms = 0;
     B200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e.device));
@@ -75,7 +88,9 @@ extern "C" int32_t b200_measure_int_peak(int32_t kind, double* gops) {
         else if (kind == 1) k_int_peak<1><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         else if (kind == 2) k_int_peak<2><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         else if (kind == 3) k_int_peak<3><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
-        else k_int_peak<4><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else if (kind == 4) k_int_peak<4><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else if (kind == 5) k_int_peak<5><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else k_int_peak<6><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         e.launches++;
         B200_CUDA_TRY(cudaEventRecord(e.ev1, e.stream));
         B200_CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,79 @@
+// Lane-parallel "Fp2 VM": executes the statically scheduled Miller-loop / final-exponentiation programs produced by
+// tools/gen_pairing_vm.py.  A TEAM of kVmTeam lanes shares one register file of Fp2 slots (shared memory on the
+// device); in every round each lane executes at most one Fp2 instruction, rounds are separated by a barrier.
+// Register allocation guarantees that no slot is both read and written in the same round.
+#pragma once
+#include "fp12.cuh"
+#include "pairing_vm_prog.cuh"
+
+namespace b200 {
+
+enum VmOp : uint32_t { VM_NOP = 0, VM_MUL, VM_SQR, VM_MULFP, VM_INV, VM_ADD, VM_SUB, VM_NEG, VM_DBL, VM_CONJ, VM_MULXI, VM_COPY, VM_LDC };
+
+// register-file accessors: dense array of Fp2 (host) or 25-word-strided shared memory (device, bank-conflict free)
+struct VmRfDense {
+    Fp2* p;
+    B200_HD Fp2 load(uint32_t i) const { return p[i]; }
+    B200_HD void store(uint32_t i, const Fp2& v) const { p[i] = v; }
+};
+constexpr int kVmSlotWords = 25;
+struct VmRfStrided {
+    uint32_t* p;
+    B200_HD Fp2 load(uint32_t i) const {
+        Fp2 v;
+        const uint32_t* q = p + i * kVmSlotWords;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { v.c0.l[k] = q[k]; v.c1.l[k] = q[12 + k]; }
+        return v;
+    }
+    B200_HD void store(uint32_t i, const Fp2& v) const {
+        uint32_t* q = p + i * kVmSlotWords;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { q[k] = v.c0.l[k]; q[12 + k] = v.c1.l[k]; }
+    }
+};
+
+// one instruction: result into `res`, returns false for NOP
+template <class RF>
+B200_HD bool vm_exec(uint32_t w, const RF& rf, const Fp2* consts, Fp2& res) {
+    const uint32_t op = w & 0xffu, a = (w >> 16) & 0xffu, b = w >> 24;
+    switch (op) {
+    case VM_NOP: return false;
+    case VM_MUL: { const Fp2 x = rf.load(a), y = rf.load(b); fp2_mul(res, x, y); } break;
+    case VM_SQR: { const Fp2 x = rf.load(a); fp2_sqr(res, x); } break;
+    case VM_MULFP: { const Fp2 x = rf.load(a); const Fp k = rf.load(b).c0; fp2_mul_fp(res, x, k); } break;
+    case VM_INV: { const Fp2 x = rf.load(a); fp2_inv(res, x); } break;
+    case VM_ADD: { const Fp2 x = rf.load(a), y = rf.load(b); fp2_add(res, x, y); } break;
+    case VM_SUB: { const Fp2 x = rf.load(a), y = rf.load(b); fp2_sub(res, x, y); } break;
+    case VM_NEG: { const Fp2 x = rf.load(a); fp2_neg(res, x); } break;
+    case VM_DBL: { const Fp2 x = rf.load(a); fp2_dbl(res, x); } break;
+    case VM_CONJ: { const Fp2 x = rf.load(a); fp2_conj(res, x); } break;
+    case VM_MULXI: { const Fp2 x = rf.load(a); fp2_mul_xi(res, x); } break;
+    case VM_COPY: res = rf.load(a); break;
+    default: res = consts[a]; break;  // VM_LDC
+    }
+    return true;
+}
+
+// Sequential reference executor (host tests): all lanes of a round read before any writes.
+inline void vm_run_host(const uint32_t* code, int n_rounds, const Fp2* consts, Fp2* rf_mem) {
+    VmRfDense rf{rf_mem};
+    for (int r = 0; r < n_rounds; r++) {
+        Fp2 res[kVmTeam];
+        bool live[kVmTeam];
+        for (int l = 0; l < kVmTeam; l++) live[l] = vm_exec(code[r * kVmTeam + l], rf, consts, res[l]);
+        for (int l = 0; l < kVmTeam; l++)
+            if (live[l]) rf.store((code[r * kVmTeam + l] >> 8) & 0xffu, res[l]);
+    }
+}
+
+// plain-integer constant table -> Montgomery form
+B200_HD void vm_const_to_mont(Fp2& out, const uint32_t limbs[24]) {
+    Fp a, b;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { a.l[i] = limbs[i]; b.l[i] = limbs[12 + i]; }
+    fp_to_mont(out.c0, a);
+    fp_to_mont(out.c1, b);
+}
+
+}  // namespace b200

@@ -177,3 +177,41 @@ extern "C" HM int hm_fp_mul_emul_matches(const uint32_t* a, const uint32_t* b) {
     fp_reduce_once(got);
     return fp_eq(want, got);
 }
+
+// ---- Fp2 VM (lane-parallel pairing programs) on the host: scheduled program == direct evaluation, bit for bit
+#include "../../ethereum_consensus_b200/csrc/pairing_vm.cuh"
+static void vm_consts(Fp2* c) { for (int i = 0; i < kVmConsts; i++) vm_const_to_mont(c[i], h_vm_consts[i]); }
+extern "C" HM int hm_vm_matches_direct(const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b) {
+    Fp2 consts[kVmConsts];
+    vm_consts(consts);
+    G1Aff p[2]; G2Aff q[2];
+    g1_in(p[0], g1a, 0); g2_in(q[0], g2a, 0); g1_in(p[1], g1b, 0); g2_in(q[1], g2b, 0);
+    Fp12 direct[2], viavm[2];
+    int ok = 1;
+    for (int k = 0; k < 2; k++) {
+        miller_loop(direct[k], p[k], q[k]);
+        static Fp2 rf[256];
+        rf[0].c0 = p[k].x; rf[0].c1 = fp_zero(); rf[1].c0 = p[k].y; rf[1].c1 = fp_zero(); rf[2] = q[k].x; rf[3] = q[k].y;
+        vm_run_host(h_miller_code, kMillerRounds, consts, rf);
+        Fp12& f = viavm[k];
+        f.c0.c0 = rf[kMillerOut[0]]; f.c1.c0 = rf[kMillerOut[1]]; f.c0.c1 = rf[kMillerOut[2]];
+        f.c1.c1 = rf[kMillerOut[3]]; f.c0.c2 = rf[kMillerOut[4]]; f.c1.c2 = rf[kMillerOut[5]];
+        const Fp2* d = &direct[k].c0.c0; const Fp2* v = &viavm[k].c0.c0;
+        for (int i = 0; i < 6; i++) if (!fp2_eq(d[i], v[i])) ok = 0;
+    }
+    // final exponentiation program: verdict and value
+    Fp12 prod;
+    fp12_mul(prod, direct[0], direct[1]);
+    const int want_one = final_exp_is_one(prod);
+    static Fp2 rf[256];
+    const Fp12* fs[2] = {&viavm[0], &viavm[1]};
+    for (int k = 0; k < 2; k++) {
+        rf[6 * k + 0] = fs[k]->c0.c0; rf[6 * k + 1] = fs[k]->c1.c0; rf[6 * k + 2] = fs[k]->c0.c1;
+        rf[6 * k + 3] = fs[k]->c1.c1; rf[6 * k + 4] = fs[k]->c0.c2; rf[6 * k + 5] = fs[k]->c1.c2;
+    }
+    vm_run_host(h_final_code, kFinalRounds, consts, rf);
+    int is_one = fp2_eq(rf[kFinalOut[0]], fp2_one());
+    for (int i = 1; i < 6; i++) is_one = is_one && fp2_is_zero(rf[kFinalOut[i]]);
+    if (is_one != want_one) ok = 0;
+    return ok | (is_one << 1);
+}

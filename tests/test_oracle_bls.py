@@ -184,3 +184,15 @@ def test_fp_mul_ptx_emulation(host_math):
     cases = [(a, b) for a in edge for b in edge] + [(rnd.randrange(bo.P), rnd.randrange(bo.P)) for _ in range(20000)]
     for a, b in cases:
         assert host_math.hm_fp_mul_emul_matches(lim(a), lim(b)) == 1
+
+
+def test_pairing_vm_programs_match_direct_evaluation(host_math):
+    """The statically scheduled lane-parallel Miller / final-exponentiation programs (tools/gen_pairing_vm.py), run by
+    the product's interpreter on the host, reproduce miller_loop bit for bit and final_exp_is_one's verdict."""
+    enc1 = lambda a: _b48(a[0]) + _b48(a[1])  # noqa: E731
+    enc2 = lambda a: _b48(a[0][0]) + _b48(a[0][1]) + _b48(a[1][0]) + _b48(a[1][1])  # noqa: E731
+    g1 = lambda k: bo.pt_to_affine(F1, bo.pt_mul(F1, bo.pt_from_affine(F1, bo.G1_GEN), k))  # noqa: E731
+    g2 = lambda k: bo.pt_to_affine(F2, bo.pt_mul(F2, bo.pt_from_affine(F2, bo.G2_GEN), k))  # noqa: E731
+    a, b = 0xabcdef123, 0x987654321
+    assert host_math.hm_vm_matches_direct(enc1(g1(a)), enc2(g2(b)), enc1(g1(bo.R - a * b % bo.R)), enc2(bo.G2_GEN)) == 3
+    assert host_math.hm_vm_matches_direct(enc1(g1(a)), enc2(g2(b)), enc1(g1(bo.R - a * b % bo.R + 5)), enc2(bo.G2_GEN)) == 1
