@@ -20,9 +20,8 @@
 namespace b200 {
 namespace {
 
-template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
-                                                                G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
+__device__ __forceinline__ void g1_validate_body(const uint8_t* __restrict__ keys, uint32_t n, G1Aff* __restrict__ out,
+                                                 int32_t* __restrict__ codes) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t b[48];
@@ -33,6 +32,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_g1_validate(const uint8_t* __
     const int32_t rc = g1_key_validate(p, b);
     codes[i] = rc;
     if (rc == BLS_SUCCESS) out[i] = p;
+}
+// Default: 256-thread CTAs, one per SM, capped at 224 registers: 224 x 256 = 57 344 registers leave exactly one
+// 32-thread x 256-register CTA of the signature / message kernels room on the same SM, so those latency-bound kernels
+// run *under* this one instead of after it (__maxnreg__ cannot be combined with __launch_bounds__).
+__global__ void __maxnreg__(224) k_g1_validate_main(const uint8_t* __restrict__ keys, uint32_t n, G1Aff* __restrict__ out,
+                                                    int32_t* __restrict__ codes) {
+    g1_validate_body(keys, n, out, codes);
+}
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
+                                                                G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
+    g1_validate_body(keys, n, out, codes);
 }
 
 constexpr int kAggWarps = 4;
@@ -135,9 +146,10 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
 
 }  // namespace
 
-// tuning knob (B200_G1_VARIANT): threads x min CTAs/SM = 0: 256x1, 1: 128x2, 2: 128x3, 3: 256x2, 4: 128x4
+// tuning knob (B200_G1_VARIANT): 0: 256 threads, 224 registers (default); threads x min CTAs/SM = 1: 128x2, 2: 128x3,
+// 3: 256x2, 4: 128x4, 5: 256x1 uncapped
 static int g_g1_variant = 0;
-void set_g1_variant(int v) { if (v >= 0 && v <= 4) g_g1_variant = v; }
+void set_g1_variant(int v) { if (v >= 0 && v <= 5) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -146,7 +158,8 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
     case 2: k_g1_validate<128, 3><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
     case 3: k_g1_validate<256, 2><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
     case 4: k_g1_validate<128, 4><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
-    default: k_g1_validate<256, 1><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
+    case 5: k_g1_validate<256, 1><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
+    default: k_g1_validate_main<<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
     }
 }
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,

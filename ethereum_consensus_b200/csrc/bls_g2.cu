@@ -13,7 +13,7 @@
 namespace b200 {
 namespace {
 
-__global__ void __launch_bounds__(64) k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
+__global__ void __launch_bounds__(32) k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
                                                        int32_t* __restrict__ sig_code) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -31,12 +31,23 @@ __global__ void __launch_bounds__(64) k_g2_sig_decode(const uint8_t* __restrict_
     sig_code[i] = rc;
 }
 
-__global__ void __launch_bounds__(64) k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ moff,
-                                                    uint32_t n, G2Aff* __restrict__ out) {
+// hash_to_G2 in two launches: the two SSWU maps of a message are independent (2n threads), then one thread per message
+// adds them, clears the cofactor and normalises.
+__global__ void __launch_bounds__(32) k_hash_to_g2_map(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ moff,
+                                                        uint32_t n, G2Jac* __restrict__ tmp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const uint32_t m = i >> 1;
+    G2Jac q;
+    hash_to_g2_map(q, msgs + moff[m], size_t(moff[m + 1] - moff[m]), int(i & 1));
+    tmp[i] = q;
+}
+__global__ void __launch_bounds__(32) k_hash_to_g2_finish(const G2Jac* __restrict__ tmp, uint32_t n, G2Aff* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const G2Jac q0 = tmp[2 * i], q1 = tmp[2 * i + 1];
     G2Aff h;
-    hash_to_g2(h, msgs + moff[i], size_t(moff[i + 1] - moff[i]));
+    hash_to_g2_finish(h, q0, q1);
     out[i] = h;
 }
 
@@ -85,11 +96,13 @@ __global__ void __launch_bounds__(32) k_g2_sum_compress(const G2Aff* __restrict_
 
 void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream) {
     if (!n) return;
-    k_g2_sig_decode<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
+    k_g2_sig_decode<<<(n + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
 }
-void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* stream) {
+void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, void* stream) {
     if (!n) return;
-    k_hash_to_g2<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, out);
+    G2Jac* tmp = static_cast<G2Jac*>(tmp_jac);
+    k_hash_to_g2_map<<<(2 * n + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, tmp);
+    k_hash_to_g2_finish<<<(n + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(tmp, n, out);
 }
 void launch_g2_sum_compress(const G2Aff* sigs, const int32_t* sig_code, uint32_t n, uint8_t* out96, int32_t* out_code, void* stream) {
     k_g2_sum_compress<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sigs, sig_code, n, out96, out_code);

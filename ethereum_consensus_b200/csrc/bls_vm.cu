@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(128) k_vm_miller(const uint32_t* __restrict__ 
     }
     __syncwarp();
     vm_run(code, kMillerRounds, consts, rf, lane, active && !trivial);
+    static_assert(kVmTeam >= 6, "team must cover the six output coefficients");
     if (active && lane < 6) {
         // w-power order of the program outputs -> tower slots c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2
         Fp2 v;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(128) k_vm_miller(const uint32_t* __restrict__ 
 }
 
 // one team per tuple (two Miller values per tuple: pairs pair_off[t], pair_off[t]+1)
-__global__ void __launch_bounds__(64) k_vm_final(const uint32_t* __restrict__ code, const Fp2* __restrict__ consts,
+__global__ void __launch_bounds__(128) k_vm_final(const uint32_t* __restrict__ code, const Fp2* __restrict__ consts,
                                                   const Fp12* __restrict__ f, const uint32_t* __restrict__ pair_off,
                                                   const int32_t* __restrict__ pk_code, const uint32_t* __restrict__ flags,
                                                   const int32_t* __restrict__ sig_code, uint32_t n_tuples,
@@ -94,10 +95,12 @@ __global__ void __launch_bounds__(64) k_vm_final(const uint32_t* __restrict__ co
         else if (flags[t] != 0 || sig_code[t] == SIG_NOT_IN_GROUP) code_out = BLS_VERIFY_FAIL;
         else active = true;
     }
-    if (active && lane < 12) {
-        const Fp2* src = reinterpret_cast<const Fp2*>(f + pair_off[t] + lane / 6);
+    if (active) {
         const int tower_pos[6] = {0, 3, 1, 4, 2, 5};
-        rf.store(lane, src[tower_pos[lane % 6]]);
+        for (uint32_t k = lane; k < 12; k += kVmTeam) {
+            const Fp2* src = reinterpret_cast<const Fp2*>(f + pair_off[t] + k / 6);
+            rf.store(k, src[tower_pos[k % 6]]);
+        }
     }
     __syncwarp();
     vm_run(code, kFinalRounds, consts, rf, lane, active);
@@ -131,8 +134,8 @@ int vm_init(void* stream) {
     cudaMemcpyAsync(g_d_final_code, h_final_code, sizeof(h_final_code), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_plain, h_vm_consts, sizeof(h_vm_consts), cudaMemcpyHostToDevice, st);
     k_vm_consts<<<1, 32, 0, st>>>(d_plain, g_d_consts);
-    cudaFuncSetAttribute(k_vm_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kMillerSlots * kVmSlotWords * 4);
-    cudaFuncSetAttribute(k_vm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kFinalSlots * kVmSlotWords * 4);
+    cudaFuncSetAttribute(k_vm_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 / kVmTeam) * kMillerSlots * kVmSlotWords * 4);
+    cudaFuncSetAttribute(k_vm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 / kVmTeam) * kFinalSlots * kVmSlotWords * 4);
     if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
     cudaFree(d_plain);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -150,7 +153,7 @@ void launch_vm_miller(const G1Aff* g1, const uint32_t* g1_idx, const G2Aff* g2, 
 void launch_vm_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_code, const uint32_t* flags,
                      const int32_t* sig_code, uint32_t n_tuples, int32_t* out_codes, void* stream) {
     if (!n_tuples) return;
-    const int threads = 64, teams = threads / kVmTeam;
+    const int threads = 128, teams = threads / kVmTeam;
     const size_t smem = size_t(teams) * kFinalSlots * kVmSlotWords * 4;
     k_vm_final<<<(n_tuples + teams - 1) / teams, threads, smem, static_cast<cudaStream_t>(stream)>>>(
         g_d_final_code, g_d_consts, f, pair_off, pk_code, flags, sig_code, n_tuples, out_codes);

@@ -18,15 +18,17 @@
 namespace b200 {
 
 struct BlsState {
-    cudaStream_t sb = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
-    DevBuf keys, key_aff, key_code, g1pts, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out;
+    cudaStream_t sb = nullptr, sc = nullptr;  // signatures / messages: high priority, run under the per-key kernel
+    cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    DevBuf keys, key_aff, key_code, g1pts, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp;
     PinnedBuf stage;
     G1Aff* d_negg1 = nullptr;
     // registry (validated keys resident on the device)
     DevBuf reg_aff, reg_code;
     size_t reg_n = 0;
     float last_dominant_ms = 0.f;
+    bool trace = false;          // B200_BLS_TRACE=1: per-phase CUDA-event timings on stderr
+    cudaEvent_t ev_t[8] = {nullptr};
     bool use_vm = true;  // lane-parallel pairing kernels (B200_PAIRING_VM=0 selects the one-thread-per-pair kernels)
 };
 
@@ -35,7 +37,13 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         BlsState* s = new BlsState();
         if (const char* v = getenv("B200_G1_VARIANT")) set_g1_variant(atoi(v));
         if (const char* v = getenv("B200_PAIRING_VM")) s->use_vm = atoi(v) != 0;
-        B200_CUDA_TRY(cudaStreamCreateWithFlags(&s->sb, cudaStreamNonBlocking));
+        if (const char* v = getenv("B200_BLS_TRACE")) s->trace = atoi(v) != 0;
+        for (auto& ev : s->ev_t) B200_CUDA_TRY(cudaEventCreate(&ev));
+        int prio_lo = 0, prio_hi = 0;
+        B200_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sb, cudaStreamNonBlocking, prio_hi));
+        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sc, cudaStreamNonBlocking, prio_hi));
+        B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_c, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreate(&s->ev_k0));
@@ -95,6 +103,7 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     B200_CUDA_TRY(s.msgs.reserve(size_t(msg_bytes) + 64));
     B200_CUDA_TRY(s.f.reserve(size_t(n_pairs + 1) * sizeof(Fp12)));
     B200_CUDA_TRY(s.out.reserve(size_t(T + 1) * 4));
+    B200_CUDA_TRY(s.h2c_tmp.reserve(size_t(2 * n_msgs + 2) * sizeof(G2Jac)));
 
     // ---- small host-built arrays, one staged copy: [key_off | index | msg_off | g1_idx | g2_idx | pair_tuple | pair_off]
     const uint32_t n_koff = (mode == MODE_FAST_AGGREGATE) ? T + 1 : 2;
@@ -132,28 +141,28 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     memcpy(s.stage.p, small.data(), small_bytes);
     int32_t* h_out = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(s.stage.p) + ((small_bytes + 15) & ~size_t(15)));
 
-    cudaStream_t sa = e.stream, sb = s.sb;
+    cudaStream_t sa = e.stream, sb = s.sb, sc = s.sc;
     uint32_t* d_small = static_cast<uint32_t*>(s.small.p);
     G1Aff* d_g1 = static_cast<G1Aff*>(s.g1pts.p);
     G2Aff* d_g2 = static_cast<G2Aff*>(s.g2pts.p);
     const G1Aff* key_aff = registry ? static_cast<const G1Aff*>(s.reg_aff.p) : static_cast<const G1Aff*>(s.key_aff.p);
     const int32_t* key_code = registry ? static_cast<const int32_t*>(s.reg_code.p) : static_cast<const int32_t*>(s.key_code.p);
 
-    // ---- stream B: signatures + messages
-    B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
-    B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));  // orders after any previous call's use of the buffers
-    if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
-    if (msg_bytes) B200_CUDA_TRY(cudaMemcpyAsync(s.msgs.p, msgs, msg_bytes, cudaMemcpyHostToDevice, sb));
-    // ---- stream A: small arrays, keys
+    // ---- small arrays first (stream A), then signatures (stream B) and messages (stream C) are launched BEFORE the
+    //      wide per-key kernel so their few, long-running CTAs are already resident when it floods the SMs
     B200_CUDA_TRY(cudaMemcpyAsync(d_small, s.stage.p, small_bytes, cudaMemcpyHostToDevice, sa));
-    if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
-    B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));  // msg_off lives in d_small
-    B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
+    B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
+    B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
+    if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
+    if (msg_bytes) B200_CUDA_TRY(cudaMemcpyAsync(s.msgs.p, msgs, msg_bytes, cudaMemcpyHostToDevice, sc));
     launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), sb);
-    launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, sb);
-    e.launches += (T ? 1 : 0) + (n_msgs ? 1 : 0);
+    launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, s.h2c_tmp.p, sc);
+    e.launches += (T ? 1 : 0) + (n_msgs ? 2 : 0);
     B200_CUDA_TRY(cudaEventRecord(s.ev_b, sb));
+    B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
+    if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
+    B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
 
     // ---- stream A: public keys
     B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
@@ -163,6 +172,7 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
         e.launches++;
     }
     B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
+    if (s.trace) cudaEventRecord(s.ev_t[0], sa);
     const uint32_t n_agg_tuples = (mode == MODE_FAST_AGGREGATE) ? T : 1;
     launch_g1_aggregate(key_aff, key_code, registry ? d_small + o_index : nullptr, d_small + o_koff, n_agg_tuples,
                         mode == MODE_FAST_AGGREGATE ? d_g1 : nullptr, static_cast<int32_t*>(s.pk_code.p),
@@ -177,7 +187,10 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
         pair_g1 = ka;  // len(msgs) != len(pks) or no keys: flagged EMPTY above -> VERIFY_FAIL after the decoding checks
     }
     // ---- join, pairing
+    if (s.trace) cudaEventRecord(s.ev_t[1], sa);
     B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_b, 0));
+    B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_c, 0));
+    if (s.trace) cudaEventRecord(s.ev_t[2], sa);
     const uint32_t* d_g1i = d_small + o_g1i;
     const uint32_t* d_g2i = d_g1i + n_pairs;
     const uint32_t* d_ptu = d_g2i + n_pairs;
@@ -186,6 +199,7 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
         launch_vm_miller(pair_g1, d_g1i, d_g2, d_g2i, d_ptu, static_cast<const int32_t*>(s.pk_code.p),
                          static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), n_pairs,
                          static_cast<Fp12*>(s.f.p), sa);
+        if (s.trace) cudaEventRecord(s.ev_t[3], sa);
         launch_vm_final(static_cast<const Fp12*>(s.f.p), d_poff, static_cast<const int32_t*>(s.pk_code.p),
                         static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), T,
                         static_cast<int32_t*>(s.out.p), sa);
@@ -203,8 +217,17 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     B200_CUDA_TRY(cudaMemcpyAsync(h_out + 4, s.out.p, size_t(T) * 4, cudaMemcpyDeviceToHost, sa));
     B200_CUDA_TRY(cudaStreamSynchronize(sa));
     B200_CUDA_TRY(cudaStreamSynchronize(sb));
+    B200_CUDA_TRY(cudaStreamSynchronize(sc));
     B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, s.ev_k0, s.ev_k1));
     B200_CUDA_TRY(cudaEventElapsedTime(&s.last_dominant_ms, s.ev_d0, s.ev_d1));
+    if (s.trace) {
+        float a = 0, b = 0, c = 0, d = 0, f2 = 0, g2 = 0;
+        cudaEventElapsedTime(&a, s.ev_k0, s.ev_d0); cudaEventElapsedTime(&b, s.ev_t[0], s.ev_t[1]);
+        cudaEventElapsedTime(&c, s.ev_t[1], s.ev_t[2]); cudaEventElapsedTime(&d, s.ev_t[2], s.ev_t[3]);
+        cudaEventElapsedTime(&f2, s.ev_t[3], s.ev_k1); cudaEventElapsedTime(&g2, s.ev_k0, s.ev_k1);
+        fprintf(stderr, "[b200 bls] pre-K1 %.2f | K1 %.2f | K2 %.2f | wait(streamB) %.2f | miller %.2f | final %.2f | total %.2f ms\n",
+                a, s.last_dominant_ms, b, c, d, f2, g2);
+    }
     for (uint32_t t = 0; t < T; t++) out_codes[t] = h_out[4 + t];
     return B200_SUCCESS;
 }

@@ -87,6 +87,7 @@ int32_t b200_init(int32_t device) {
     B200_CUDA_TRY(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
     B200_CUDA_TRY(cudaEventCreate(&e.ev0));
     B200_CUDA_TRY(cudaEventCreate(&e.ev1));
+    for (auto& ev : e.ev_copy) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e.device = device;
     const char* a = getenv("B200_SSZ_MINB_VALIDATORS");
     const char* b = getenv("B200_SSZ_MINB_STAGE");
@@ -105,6 +106,7 @@ void b200_shutdown(void) {
     if (e.d_zero) cudaFree(e.d_zero);
     e.d_zero = nullptr;
     cudaEventDestroy(e.ev0); cudaEventDestroy(e.ev1);
+    for (auto& ev : e.ev_copy) cudaEventDestroy(ev);
     cudaStreamDestroy(e.stream); cudaStreamDestroy(e.copy_stream);
     e.ready = false;
 }

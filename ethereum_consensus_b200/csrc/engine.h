@@ -48,6 +48,7 @@ struct Engine {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_copy[17] = {nullptr};  // H2D slice k done (copy stream) -> compute stream may hash slice k
     std::mutex mu;
     std::string last_error;
     uint64_t launches = 0;

@@ -125,6 +125,21 @@ B200_BIG void iso3_map(G2Jac& out, const Fp2& x, const Fp2& y) {
     if (fp2_is_zero(out.z)) jac_set_inf(out);
 }
 
+// first half, for j in {0, 1}: u_j = hash_to_field(msg)[j], Q_j = iso3(sswu(u_j)) in Jacobian coordinates
+B200_BIG void hash_to_g2_map(G2Jac& out, const uint8_t* msg, size_t len, int j) {
+    Fp2 u0, u1, x, y;
+    hash_to_field_fp2(u0, u1, msg, len);
+    sswu_map(x, y, j ? u1 : u0);
+    iso3_map(out, x, y);
+}
+// second half: Q_0 + Q_1, clear the cofactor, normalise
+B200_BIG void hash_to_g2_finish(G2Aff& out, const G2Jac& q0, const G2Jac& q1) {
+    G2Jac s, c;
+    jac_add(s, q0, q1);
+    g2_clear_cofactor(c, s);
+    jac_to_aff(out, c);
+}
+
 // full hash_to_curve -> affine G2 point
 B200_BIG void hash_to_g2(G2Aff& out, const uint8_t* msg, size_t len) {
     Fp2 u0, u1, x, y;

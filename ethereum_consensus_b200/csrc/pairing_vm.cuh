@@ -4,7 +4,11 @@
 // Register allocation guarantees that no slot is both read and written in the same round.
 #pragma once
 #include "fp12.cuh"
+#if defined(B200_VM_TEAM16)  // A/B knob; measured on B200: teams of 8 lanes beat 16 (profiles/r1_tuning.md)
+#include "pairing_vm_prog16.cuh"
+#else
 #include "pairing_vm_prog.cuh"
+#endif
 
 namespace b200 {
 

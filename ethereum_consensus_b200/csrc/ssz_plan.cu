@@ -64,7 +64,7 @@ uint64_t SszPlan::stage_field(const uint8_t* src, size_t nbytes) {
     uint64_t off = (field_next_ + 255) & ~uint64_t(255);
     size_t padded = ((nbytes + 31) & ~size_t(31)) + 32;
     field_next_ = off + padded;
-    if (nbytes) copies_.push_back(HostCopy{src, nbytes, off, padded - nbytes});
+    if (nbytes) copies_.push_back(HostCopy{src, nbytes, off, padded - nbytes, false});
     return off;
 }
 void SszPlan::add_job(size_t stage, const PJob& j) {
@@ -104,7 +104,10 @@ uint32_t SszPlan::wide_records(uint32_t type, uint64_t field_off, uint64_t n, in
     if (n == 0) return zero(depth_target);
     PJob j;
     j.type = type; j.src.in_arena = false; j.src.off = field_off; j.dst = arena_alloc(n); j.n_in = n;
-    if (type == JOB_VALIDATORS) validator_jobs_.push_back(j); else add_job(0, j);
+    if (type == JOB_VALIDATORS) {
+        validator_jobs_.push_back(j);
+        for (auto& c : copies_) if (c.field_off == field_off) c.validators = true;
+    } else add_job(0, j);
     PSrc s; s.in_arena = true; s.off = j.dst;
     return wide_nodes(s, false, n, 0, depth_target, 1);
 }
@@ -183,19 +186,11 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     if (sz_wend) memcpy(st + off_wend, wave_end.data(), sz_wend);
 
     cudaStream_t s = e.stream;
-    if (!fields_resident)
-        for (auto& c : copies_) {
-            B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off, c.src, c.nbytes, cudaMemcpyHostToDevice, s));
-            if (c.nbytes % 32)
-                B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, s));
-        }
+    uint8_t* d_plan = static_cast<uint8_t*>(planbuf.p);
     B200_CUDA_TRY(cudaMemcpyAsync(d_arena, e.d_zero, 65 * 32, cudaMemcpyDeviceToDevice, s));
     if (sz_small) B200_CUDA_TRY(cudaMemcpyAsync(d_arena + kSmallBase * 8, st, sz_small, cudaMemcpyHostToDevice, s));
-    uint8_t* d_plan = static_cast<uint8_t*>(planbuf.p);
     if (sz_ops + sz_wend)
         B200_CUDA_TRY(cudaMemcpyAsync(d_plan + off_ops, st + off_ops, off_out - off_ops, cudaMemcpyHostToDevice, s));
-
-    B200_CUDA_TRY(cudaEventRecord(e.ev0, s));
     auto materialize = [&](const PJob& pj) {
         Job j{};
         j.src = pj.src.in_arena ? static_cast<const void*>(d_arena + pj.src.off * 8)
@@ -204,7 +199,46 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         j.n_in = pj.n_in; j.type = pj.type; j.level = pj.level; j.nlev = pj.nlev; j.raw = pj.raw;
         return j;
     };
-    for (auto& pj : validator_jobs_) { launch_validators(materialize(pj), s); e.launches++; }
+    B200_CUDA_TRY(cudaEventRecord(e.ev0, s));
+    bool validators_launched = false;
+    if (!fields_resident) {
+        // H2D on the copy stream; the Validator list (85 % of the bytes) goes first, in up to 16 slices, and the compute
+        // stream hashes slice k as soon as its copy has landed: kernels hide under the PCIe transfer.
+        cudaStream_t cs = e.copy_stream;
+        B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], s));
+        B200_CUDA_TRY(cudaStreamWaitEvent(cs, e.ev_copy[16], 0));  // buffers may still be in use by the previous call
+        for (auto& c : copies_) {
+            if (!c.validators || validator_jobs_.size() != 1) continue;
+            const PJob& pj = validator_jobs_[0];
+            const uint64_t n = pj.n_in;
+            const uint64_t per = ((n + 15) / 16 + kStageThreads - 1) / kStageThreads * kStageThreads;  // whole CTAs per slice
+            int k = 0;
+            for (uint64_t lo = 0; lo < n; lo += per, k++) {
+                const uint64_t cnt = std::min(per, n - lo);
+                B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off + lo * 121, c.src + lo * 121, cnt * 121, cudaMemcpyHostToDevice, cs));
+                B200_CUDA_TRY(cudaEventRecord(e.ev_copy[k], cs));
+                B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[k], 0));
+                Job j = materialize(pj);
+                j.src = d_fields + c.field_off + lo * 121;
+                j.dst = d_arena + (pj.dst + lo) * 8;
+                j.n_in = cnt;
+                launch_validators(j, s);
+                e.launches++;
+            }
+            if (c.nbytes % 32) B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, cs));
+            validators_launched = true;
+        }
+        for (auto& c : copies_) {
+            if (c.validators && validators_launched) continue;
+            B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off, c.src, c.nbytes, cudaMemcpyHostToDevice, cs));
+            if (c.nbytes % 32)
+                B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, cs));
+        }
+        B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], cs));
+        B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[16], 0));
+    }
+    if (!validators_launched)
+        for (auto& pj : validator_jobs_) { launch_validators(materialize(pj), s); e.launches++; }
     for (auto& stage : stages_) {
         // split into launches of at most kMaxJobsPerStage jobs
         for (size_t b = 0; b < stage.size(); b += kMaxJobsPerStage) {

@@ -33,6 +33,7 @@ struct HostCopy {
     size_t nbytes;
     uint64_t field_off;
     size_t zero_tail;  // bytes to clear after the copy (keeps the last partial chunk zero-padded)
+    bool validators = false;  // the big Validator list: copied in slices so hashing overlaps the PCIe transfer
 };
 
 class SszPlan {

@@ -293,7 +293,7 @@ def final_exp(cx, f1, f2):
 
 
 # ------------------------------------------------------------------------------------------------ schedule + allocate
-def schedule(tr, outputs, team):
+def schedule(tr, outputs, team, window=None):
     ins = tr.ins
     producer = {d: i for i, (_, d, _, _) in enumerate(ins)}
     # dead-code elimination from the outputs
@@ -329,9 +329,22 @@ def schedule(tr, outputs, team):
     ready = [i for i in idx if remaining[i] == 0]
     rounds = []
     done_round = {}
+    pos = {i: k for k, i in enumerate(idx)}          # program order
+    unscheduled = set(idx)
+    import heapq
+    order_heap = list(idx)
+    heapq.heapify(order_heap)
     while ready:
+        # sliding window over program order: bounds how far ahead of the oldest pending instruction we run,
+        # which bounds live ranges (register-file slots = shared memory per team = occupancy)
+        while order_heap and order_heap[0] not in unscheduled:
+            heapq.heappop(order_heap)
+        oldest = pos[order_heap[0]] if order_heap else 0
+        cand = [i for i in ready if window is None or pos[i] - oldest < window]
+        if not cand:
+            cand = [min(ready, key=lambda i: pos[i])]
         classes = {}
-        for i in ready:
+        for i in cand:
             op = ins[i][0]
             cl = HEAVY.get(op, "light")
             classes.setdefault(cl, []).append(i)
@@ -345,6 +358,7 @@ def schedule(tr, outputs, team):
         rounds.append(pick)
         for i in pick:
             ready.remove(i)
+            unscheduled.discard(i)
             done_round[i] = r
         for i in pick:
             for u in users[i]:
@@ -417,14 +431,14 @@ def run_program(rounds, nslots, inputs):
 def flat12(f): return [f[0][0], f[1][0], f[0][1], f[1][1], f[0][2], f[1][2]]
 
 
-def build(team):
+def build(team, window=None, window_final=None):
     # ---- Miller loop: inputs xP, yP (as Fp2 with c1 = 0), Qx, Qy
     tr = Tracer()
     cx = Ctx(tr)
     xp, yp, qx, qy = tr.input(), tr.input(), tr.input(), tr.input()
     f = miller_loop(cx, xp, yp, qx, qy)
     outs = [v.id for v in flat12(f)]
-    m_rounds, m_slot, m_nslots = schedule(tr, outs, team)
+    m_rounds, m_slot, m_nslots = schedule(tr, outs, team, window)
     m_out = [m_slot[o] for o in outs]
     # ---- final exponentiation: inputs f1, f2 (w-power order)
     tr2 = Tracer()
@@ -434,7 +448,7 @@ def build(team):
     mk = lambda s: ((s[0], s[2], s[4]), (s[1], s[3], s[5]))  # noqa: E731
     c = final_exp(cx2, mk(i1), mk(i2))
     outs2 = [v.id for v in flat12(c)]
-    f_rounds, f_slot, f_nslots = schedule(tr2, outs2, team)
+    f_rounds, f_slot, f_nslots = schedule(tr2, outs2, team, window_final if window_final is not None else window)
     f_out = [f_slot[o] for o in outs2]
     return (m_rounds, m_nslots, m_out), (f_rounds, f_nslots, f_out)
 
@@ -499,14 +513,18 @@ def emit(team, miller, final):
         limbs = [(c[0] >> (32 * i)) & 0xffffffff for i in range(12)] + [(c[1] >> (32 * i)) & 0xffffffff for i in range(12)]
         out.append("    {" + ", ".join(f"0x{v:08x}u" for v in limbs) + "},\n")
     out.append("};\n\n}  // namespace b200\n")
-    path = ROOT / "ethereum_consensus_b200" / "csrc" / "pairing_vm_prog.cuh"
+    path = ROOT / "ethereum_consensus_b200" / "csrc" / ("pairing_vm_prog.cuh" if team == 8 else f"pairing_vm_prog{team}.cuh")
     path.write_text("".join(out))
     return path
 
 
 def main():
-    team = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-    miller, final = build(team)
+    team = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    # scheduling windows (Miller, final): measured trade-off between heavy rounds and register-file slots, see
+    # profiles/r1_tuning.md; defaults: team 16 -> (256, 48), team 8 -> (96, 96)
+    window = int(sys.argv[2]) if len(sys.argv) > 2 else (256 if team == 16 else 96)
+    window_final = int(sys.argv[3]) if len(sys.argv) > 3 else (48 if team == 16 else 96)
+    miller, final = build(team, window, window_final)
     for name, (rounds, nslots, _o) in (("miller", miller), ("final", final)):
         heavy = [r for r in rounds if r and r[0][0] in HEAVY]
         util = sum(len(r) for r in heavy) / max(1, len(heavy) * team)
