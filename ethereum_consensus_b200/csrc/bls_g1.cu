@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(32 * kAggWarps) k_g1_aggregate(const G1Aff* __
                                                                   const int32_t* __restrict__ key_codes,
                                                                   const uint32_t* __restrict__ index,
                                                                   const uint32_t* __restrict__ off, uint32_t n_tuples,
-                                                                  G1Aff* __restrict__ agg, int32_t* __restrict__ pk_code,
+                                                                  G1Aff* __restrict__ agg, G1Pre* __restrict__ agg_pre,
+                                                                  int32_t* __restrict__ pk_code,
                                                                   uint32_t* __restrict__ flags, uint32_t extra_flags) {
     __shared__ G1Jac part[kAggWarps][32];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(32 * kAggWarps) k_g1_aggregate(const G1Aff* __
         }
         return;
     }
-    if (agg == nullptr) {  // code scan only
+    if (agg == nullptr && agg_pre == nullptr) {  // code scan only
         if (lane == 0) { pk_code[t] = BLS_SUCCESS; flags[t] = (hi == lo ? TUPLE_FLAG_EMPTY : 0u) | extra_flags; }
         return;
     }
@@ -94,23 +95,41 @@ __global__ void __launch_bounds__(32 * kAggWarps) k_g1_aggregate(const G1Aff* __
         __syncwarp();
     }
     if (lane == 0) {
-        G1Aff a;
-        jac_to_aff(a, part[warp][0]);
-        agg[t] = a;
+        bool inf;
+        if (agg_pre) {   // hand the Jacobian sum to the Miller VM: (X Z, Y, Z^3), no inversion
+            const G1Jac s = part[warp][0];
+            G1Pre p;
+            inf = jac_is_inf(s);
+            Fp zz;
+            fp_sqr(zz, s.z);
+            fp_mul(p.z3, zz, s.z);
+            fp_mul(p.xz, s.x, s.z);
+            p.y = s.y;
+            p.inf = inf ? 1u : 0u;
+            agg_pre[t] = p;
+        } else {
+            G1Aff a;
+            jac_to_aff(a, part[warp][0]);
+            agg[t] = a;
+            inf = a.inf != 0;
+        }
         pk_code[t] = BLS_SUCCESS;
-        flags[t] = (hi == lo ? TUPLE_FLAG_EMPTY : 0u) | (a.inf ? TUPLE_FLAG_AGG_INF : 0u) | extra_flags;
+        flags[t] = (hi == lo ? TUPLE_FLAG_EMPTY : 0u) | (inf ? TUPLE_FLAG_AGG_INF : 0u) | extra_flags;
     }
 }
 
 __global__ void k_g1_compress(const G1Aff* p, uint8_t* out48) {
     if (threadIdx.x == 0 && blockIdx.x == 0) g1_compress(out48, *p);
 }
-__global__ void k_neg_g1(G1Aff* out) {
+__global__ void k_neg_g1(G1Aff* out, G1Pre* out_pre) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         G1Aff g;
         const Fp x = B200_FP_G1_X, y = B200_FP_G1_NEG_Y;
         g.x = x; g.y = y; g.inf = 0;
         *out = g;
+        G1Pre p;
+        p.xz = x; p.y = y; p.z3 = fp_one(); p.inf = 0;
+        *out_pre = p;
     }
 }
 
@@ -163,16 +182,16 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
     }
 }
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,
-                         uint32_t n_tuples, G1Aff* agg, int32_t* pk_code, uint32_t* flags, uint32_t extra_flags,
-                         void* stream) {
+                         uint32_t n_tuples, G1Aff* agg, G1Pre* agg_pre, int32_t* pk_code, uint32_t* flags,
+                         uint32_t extra_flags, void* stream) {
     if (!n_tuples) return;
     k_g1_aggregate<<<(n_tuples + kAggWarps - 1) / kAggWarps, 32 * kAggWarps, 0, static_cast<cudaStream_t>(stream)>>>(
-        keys, key_codes, index, off, n_tuples, agg, pk_code, flags, extra_flags);
+        keys, key_codes, index, off, n_tuples, agg, agg_pre, pk_code, flags, extra_flags);
 }
 void launch_g1_compress(const G1Aff* p, uint8_t* out48, void* stream) {
     k_g1_compress<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p, out48);
 }
-void launch_neg_g1(G1Aff* out, void* stream) { k_neg_g1<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out); }
+void launch_neg_g1(G1Aff* out, G1Pre* out_pre, void* stream) { k_neg_g1<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out, out_pre); }
 void launch_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch, void* stream) {
     k_fp_selftest<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(n, seed, out_mismatch);
 }

@@ -13,7 +13,8 @@
 namespace b200 {
 namespace {
 
-__global__ void __launch_bounds__(32) k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
+// 32-thread CTAs capped at 128 registers (4 096 per CTA): two of them fit beside a 57 344-register per-key CTA
+__global__ void __maxnreg__(128) k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
                                                        int32_t* __restrict__ sig_code) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(32) k_g2_sig_decode(const uint8_t* __restrict_
 
 // hash_to_G2 in two launches: the two SSWU maps of a message are independent (2n threads), then one thread per message
 // adds them, clears the cofactor and normalises.
-__global__ void __launch_bounds__(32) k_hash_to_g2_map(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ moff,
+__global__ void __maxnreg__(128) k_hash_to_g2_map(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ moff,
                                                         uint32_t n, G2Jac* __restrict__ tmp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(32) k_hash_to_g2_map(const uint8_t* __restrict
     hash_to_g2_map(q, msgs + moff[m], size_t(moff[m + 1] - moff[m]), int(i & 1));
     tmp[i] = q;
 }
-__global__ void __launch_bounds__(32) k_hash_to_g2_finish(const G2Jac* __restrict__ tmp, uint32_t n, G2Aff* __restrict__ out) {
+__global__ void __maxnreg__(128) k_hash_to_g2_finish(const G2Jac* __restrict__ tmp, uint32_t n, G2Aff* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const G2Jac q0 = tmp[2 * i], q1 = tmp[2 * i + 1];

@@ -8,6 +8,13 @@
 
 namespace b200 {
 
+// G1 operand of the lane-parallel Miller loop: (X Z, Y, Z^3) of a Jacobian point (affine point: (x, y, 1)); the line
+// functions absorb the Z^3 scaling, so the aggregate key is never inverted
+struct G1Pre {
+    Fp xz, y, z3;
+    uint32_t inf;
+};
+
 // per-tuple flags written by the G1 aggregation kernel
 enum : uint32_t { TUPLE_FLAG_EMPTY = 1u, TUPLE_FLAG_AGG_INF = 2u };
 // per-signature status written by the signature kernel
@@ -19,9 +26,10 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
 // K2: per tuple t, sum the validated keys [off[t], off[t+1]) (or gather through `index` when non-null);
 //     first failing key (in order) decides pk_code[t]
 //     agg == nullptr: only the code scan (aggregate_verify keeps keys separate); extra_flags is OR-ed into flags
+//     agg_pre != nullptr: write the un-normalised sum for the VM Miller kernel instead of the affine point
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,
-                         uint32_t n_tuples, G1Aff* agg, int32_t* pk_code, uint32_t* flags, uint32_t extra_flags,
-                         void* stream);
+                         uint32_t n_tuples, G1Aff* agg, G1Pre* agg_pre, int32_t* pk_code, uint32_t* flags,
+                         uint32_t extra_flags, void* stream);
 // K3: decompress + subgroup-check every 96-byte signature
 void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream);
 // K4: hash_to_G2 of message i = bytes [moff[i], moff[i+1]) of `msgs`
@@ -36,7 +44,7 @@ void launch_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_cod
                   const int32_t* sig_code, uint32_t n_tuples, int32_t* out_codes, void* stream);
 // lane-parallel (team) versions of K5 / K6 for tuples with exactly two pairs (bls_vm.cu); vm_init returns 0 on success
 int vm_init(void* stream);
-void launch_vm_miller(const G1Aff* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
+void launch_vm_miller(const G1Pre* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
                       const uint32_t* pair_tuple, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,
                       uint32_t n_pairs, Fp12* f, void* stream);
 void launch_vm_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_code, const uint32_t* flags,
@@ -44,8 +52,8 @@ void launch_vm_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_
 // aggregation helpers for `aggregate` / `eth_aggregate_public_keys`
 void launch_g2_sum_compress(const G2Aff* sigs, const int32_t* sig_code, uint32_t n, uint8_t* out96, int32_t* out_code, void* stream);
 void launch_g1_compress(const G1Aff* p, uint8_t* out48, void* stream);
-// writes -g1 (the negated generator) to *out
-void launch_neg_g1(G1Aff* out, void* stream);
+// writes -g1 (the negated generator) to *out (and its G1Pre form)
+void launch_neg_g1(G1Aff* out, G1Pre* out_pre, void* stream);
 // on-device self-test of Fp arithmetic (portable vs tuned paths), returns mismatches in *out
 void launch_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch, void* stream);
 

@@ -41,7 +41,7 @@ __device__ __forceinline__ bool tuple_dead(uint32_t t, const int32_t* pk_code, c
 
 // one team per pair
 __global__ void __launch_bounds__(128) k_vm_miller(const uint32_t* __restrict__ code, const Fp2* __restrict__ consts,
-                                                    const G1Aff* __restrict__ g1, const uint32_t* __restrict__ g1_idx,
+                                                    const G1Pre* __restrict__ g1, const uint32_t* __restrict__ g1_idx,
                                                     const G2Aff* __restrict__ g2, const uint32_t* __restrict__ g2_idx,
                                                     const uint32_t* __restrict__ pair_tuple, const int32_t* __restrict__ pk_code,
                                                     const uint32_t* __restrict__ flags, const int32_t* __restrict__ sig_code,
@@ -53,14 +53,15 @@ __global__ void __launch_bounds__(128) k_vm_miller(const uint32_t* __restrict__ 
     bool active = i < n_pairs && !tuple_dead(pair_tuple[i], pk_code, flags, sig_code);
     bool trivial = false;  // a point at infinity: the pair contributes 1
     if (active) {
-        const G1Aff* p = g1 + g1_idx[i];
+        const G1Pre* p = g1 + g1_idx[i];
         const G2Aff* q = g2 + g2_idx[i];
         trivial = p->inf || q->inf;
-        if (!trivial) {
-            if (lane == 0) { Fp2 v; v.c0 = p->x; v.c1 = fp_zero(); rf.store(0, v); }
+        if (!trivial) {  // program inputs: slots 0..4 = X Z, Y, Z^3 (as Fp2 with c1 = 0), Qx, Qy
+            if (lane == 0) { Fp2 v; v.c0 = p->xz; v.c1 = fp_zero(); rf.store(0, v); }
             if (lane == 1) { Fp2 v; v.c0 = p->y; v.c1 = fp_zero(); rf.store(1, v); }
-            if (lane == 2) rf.store(2, q->x);
-            if (lane == 3) rf.store(3, q->y);
+            if (lane == 2) { Fp2 v; v.c0 = p->z3; v.c1 = fp_zero(); rf.store(2, v); }
+            if (lane == 3) rf.store(3, q->x);
+            if (lane == 4) rf.store(4, q->y);
         }
     }
     __syncwarp();
@@ -141,7 +142,7 @@ int vm_init(void* stream) {
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-void launch_vm_miller(const G1Aff* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
+void launch_vm_miller(const G1Pre* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
                       const uint32_t* pair_tuple, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,
                       uint32_t n_pairs, Fp12* f, void* stream) {
     if (!n_pairs) return;

@@ -20,9 +20,10 @@ namespace b200 {
 struct BlsState {
     cudaStream_t sb = nullptr, sc = nullptr;  // signatures / messages: high priority, run under the per-key kernel
     cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
-    DevBuf keys, key_aff, key_code, g1pts, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp;
+    DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp;
     PinnedBuf stage;
     G1Aff* d_negg1 = nullptr;
+    G1Pre* d_negg1_pre = nullptr;
     // registry (validated keys resident on the device)
     DevBuf reg_aff, reg_code;
     size_t reg_n = 0;
@@ -51,7 +52,8 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         B200_CUDA_TRY(cudaEventCreate(&s->ev_d0));
         B200_CUDA_TRY(cudaEventCreate(&s->ev_d1));
         B200_CUDA_TRY(cudaMalloc(&s->d_negg1, sizeof(G1Aff)));
-        launch_neg_g1(s->d_negg1, e.stream);
+        B200_CUDA_TRY(cudaMalloc(&s->d_negg1_pre, sizeof(G1Pre)));
+        launch_neg_g1(s->d_negg1, s->d_negg1_pre, e.stream);
         e.launches++;
         if (vm_init(e.stream) != 0) { e.last_error = "pairing VM initialisation failed"; return B200_ERR_CUDA; }
         e.launches++;
@@ -95,6 +97,7 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     B200_CUDA_TRY(s.key_aff.reserve(size_t(n_keys + 1) * sizeof(G1Aff)));
     B200_CUDA_TRY(s.key_code.reserve(size_t(n_keys + 1) * 4));
     B200_CUDA_TRY(s.g1pts.reserve(size_t(n_g1) * sizeof(G1Aff)));
+    B200_CUDA_TRY(s.g1pre.reserve(size_t(n_g1) * sizeof(G1Pre)));
     B200_CUDA_TRY(s.pk_code.reserve(size_t(T + 1) * 4));
     B200_CUDA_TRY(s.flags.reserve(size_t(T + 1) * 4));
     B200_CUDA_TRY(s.sigs.reserve(size_t(T) * 96 + 64));
@@ -175,12 +178,15 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     if (s.trace) cudaEventRecord(s.ev_t[0], sa);
     const uint32_t n_agg_tuples = (mode == MODE_FAST_AGGREGATE) ? T : 1;
     launch_g1_aggregate(key_aff, key_code, registry ? d_small + o_index : nullptr, d_small + o_koff, n_agg_tuples,
-                        mode == MODE_FAST_AGGREGATE ? d_g1 : nullptr, static_cast<int32_t*>(s.pk_code.p),
-                        static_cast<uint32_t*>(s.flags.p), force_fail_shape ? uint32_t(TUPLE_FLAG_EMPTY) : 0u, sa);
+                        (mode == MODE_FAST_AGGREGATE && !s.use_vm) ? d_g1 : nullptr,
+                        (mode == MODE_FAST_AGGREGATE && s.use_vm) ? static_cast<G1Pre*>(s.g1pre.p) : nullptr,
+                        static_cast<int32_t*>(s.pk_code.p), static_cast<uint32_t*>(s.flags.p),
+                        force_fail_shape ? uint32_t(TUPLE_FLAG_EMPTY) : 0u, sa);
     e.launches++;
     const G1Aff* pair_g1 = d_g1;
     if (mode == MODE_FAST_AGGREGATE) {
         B200_CUDA_TRY(cudaMemcpyAsync(d_g1 + T, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
+        B200_CUDA_TRY(cudaMemcpyAsync(static_cast<G1Pre*>(s.g1pre.p) + T, s.d_negg1_pre, sizeof(G1Pre), cudaMemcpyDeviceToDevice, sa));
     } else {
         G1Aff* ka = static_cast<G1Aff*>(s.key_aff.p);
         B200_CUDA_TRY(cudaMemcpyAsync(ka + n_keys, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
@@ -196,7 +202,7 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     const uint32_t* d_ptu = d_g2i + n_pairs;
     const uint32_t* d_poff = d_ptu + n_pairs;
     if (mode == MODE_FAST_AGGREGATE && s.use_vm) {
-        launch_vm_miller(pair_g1, d_g1i, d_g2, d_g2i, d_ptu, static_cast<const int32_t*>(s.pk_code.p),
+        launch_vm_miller(static_cast<const G1Pre*>(s.g1pre.p), d_g1i, d_g2, d_g2i, d_ptu, static_cast<const int32_t*>(s.pk_code.p),
                          static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), n_pairs,
                          static_cast<Fp12*>(s.f.p), sa);
         if (s.trace) cudaEventRecord(s.ev_t[3], sa);
@@ -469,7 +475,7 @@ int32_t b200_eth_aggregate_public_keys(const uint8_t* pks_flat, size_t n, uint8_
     launch_g1_validate(static_cast<const uint8_t*>(s->keys.p), uint32_t(n), static_cast<G1Aff*>(s->key_aff.p),
                        static_cast<int32_t*>(s->key_code.p), sa);
     launch_g1_aggregate(static_cast<const G1Aff*>(s->key_aff.p), static_cast<const int32_t*>(s->key_code.p), nullptr,
-                        static_cast<const uint32_t*>(s->small.p), 1, static_cast<G1Aff*>(s->g1pts.p),
+                        static_cast<const uint32_t*>(s->small.p), 1, static_cast<G1Aff*>(s->g1pts.p), nullptr,
                         static_cast<int32_t*>(s->pk_code.p), static_cast<uint32_t*>(s->flags.p), 0u, sa);
     uint8_t* d_out = static_cast<uint8_t*>(s->out.p);
     launch_g1_compress(static_cast<const G1Aff*>(s->g1pts.p), d_out, sa);

@@ -191,7 +191,8 @@ extern "C" HM int hm_vm_matches_direct(const uint8_t* g1a, const uint8_t* g2a, c
     for (int k = 0; k < 2; k++) {
         miller_loop(direct[k], p[k], q[k]);
         static Fp2 rf[256];
-        rf[0].c0 = p[k].x; rf[0].c1 = fp_zero(); rf[1].c0 = p[k].y; rf[1].c1 = fp_zero(); rf[2] = q[k].x; rf[3] = q[k].y;
+        rf[0].c0 = p[k].x; rf[0].c1 = fp_zero(); rf[1].c0 = p[k].y; rf[1].c1 = fp_zero();
+        rf[2].c0 = fp_one(); rf[2].c1 = fp_zero(); rf[3] = q[k].x; rf[4] = q[k].y;   // affine P: (x, y, 1)
         vm_run_host(h_miller_code, kMillerRounds, consts, rf);
         Fp12& f = viavm[k];
         f.c0.c0 = rf[kMillerOut[0]]; f.c1.c0 = rf[kMillerOut[1]]; f.c0.c1 = rf[kMillerOut[2]];

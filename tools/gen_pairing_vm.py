@@ -220,23 +220,25 @@ def jac_double(t):
     return (x3, y3, z3)
 
 
-def miller_double_step(t, xp, yp):
+def miller_double_step(t, xp, yp, z3p):
+    """P enters as (xp, yp, z3p) = (X Z, Y, Z^3) of a Jacobian G1 point: the line is scaled by Z^3 in Fp (killed by the
+    final exponentiation), which saves the per-tuple inversion of the aggregate key; affine P: (x, y, 1)."""
     xx, yy, zz = t[0].sqr(), t[1].sqr(), t[2].sqr()
     e = xx.dbl().add(xx)
-    A = e.mul(t[0]).sub(yy.dbl())
+    A = e.mul(t[0]).sub(yy.dbl()).mulfp(z3p)
     B = e.mul(zz).mulfp(xp).neg()
     t2 = jac_double(t)
     C = t2[2].mul(zz).mulfp(yp)
     return t2, A, B, C
 
 
-def miller_add_step(t, q, xp, yp):
+def miller_add_step(t, q, xp, yp, z3p):
     zz = t[2].sqr()
     zzz = zz.mul(t[2])
     h = q[0].mul(zz).sub(t[0])
     rr = q[1].mul(zzz).sub(t[1])
     z3 = t[2].mul(h)
-    A = rr.mul(q[0]).sub(q[1].mul(z3))
+    A = rr.mul(q[0]).sub(q[1].mul(z3)).mulfp(z3p)
     B = rr.mulfp(xp).neg()
     C = z3.mulfp(yp)
     hh = h.sqr()
@@ -247,14 +249,14 @@ def miller_add_step(t, q, xp, yp):
     return (x3, y3, z3), A, B, C
 
 
-def miller_loop(cx, xp, yp, qx, qy):
+def miller_loop(cx, xp, yp, z3p, qx, qy):
     """f_{z,Q}(P), P, Q not at infinity (the kernels bypass the program for infinite points)."""
     one = cx.const(0)
     t = (qx, qy, one)
     q = (qx, qy)
     f = None
     for bit in range(62, -1, -1):
-        t, A, B, C = miller_double_step(t, xp, yp)
+        t, A, B, C = miller_double_step(t, xp, yp, z3p)
         if f is None:                      # first iteration: f = 1 * line
             zero_free = True
             f = ((A, B, None), (None, C, None))
@@ -263,7 +265,7 @@ def miller_loop(cx, xp, yp, qx, qy):
         if f[0][2] is None:                # materialise the sparse first value as a dense element lazily
             f = _densify(cx, f)
         if (Z_ABS >> bit) & 1:
-            t, A, B, C = miller_add_step(t, q, xp, yp)
+            t, A, B, C = miller_add_step(t, q, xp, yp, z3p)
             f = f12_mul_by_line(f, A, B, C)
     return f12_conj(f)
 
@@ -435,8 +437,8 @@ def build(team, window=None, window_final=None):
     # ---- Miller loop: inputs xP, yP (as Fp2 with c1 = 0), Qx, Qy
     tr = Tracer()
     cx = Ctx(tr)
-    xp, yp, qx, qy = tr.input(), tr.input(), tr.input(), tr.input()
-    f = miller_loop(cx, xp, yp, qx, qy)
+    xp, yp, z3p, qx, qy = tr.input(), tr.input(), tr.input(), tr.input(), tr.input()
+    f = miller_loop(cx, xp, yp, z3p, qx, qy)
     outs = [v.id for v in flat12(f)]
     m_rounds, m_slot, m_nslots = schedule(tr, outs, team, window)
     m_out = [m_slot[o] for o in outs]
@@ -460,10 +462,13 @@ def selfcheck(team, miller, final):
     cxn = Ctx(None)
     def g1(k): return bo.pt_to_affine(F1, bo.pt_mul(F1, bo.pt_from_affine(F1, bo.G1_GEN), k))
     def g2(k): return bo.pt_to_affine(F2, bo.pt_mul(F2, bo.pt_from_affine(F2, bo.G2_GEN), k))
-    def mill(pa, qa):
-        rf = run_program(m_rounds, m_nslots, [(pa[0], 0), (pa[1], 0), qa[0], qa[1]])
+    def mill(pa, qa, z=1):
+        # P handed over in Jacobian form (X, Y, Z) = (x z^2, y z^3, z): inputs (X Z, Y, Z^3)
+        X, Y = pa[0] * z * z % P, pa[1] * z * z * z % P
+        ins = [(X * z % P, 0), (Y, 0), (z * z * z % P, 0)]
+        rf = run_program(m_rounds, m_nslots, ins + [qa[0], qa[1]])
         got = [rf[s].v for s in m_out]
-        want = [x.v for x in flat12(miller_loop(cxn, Num((pa[0], 0)), Num((pa[1], 0)), Num(qa[0]), Num(qa[1])))]
+        want = [x.v for x in flat12(miller_loop(cxn, Num(ins[0]), Num(ins[1]), Num(ins[2]), Num(qa[0]), Num(qa[1])))]
         assert got == want, "scheduled Miller program != direct evaluation"
         return got
     def fin(fa, fb):
@@ -476,6 +481,7 @@ def selfcheck(team, miller, final):
     one = [(1, 0)] + [(0, 0)] * 5
     a, b = 0x1234567, 0x7654321
     assert fin(mill(g1(a), g2(b)), mill(g1(bo.R - a * b % bo.R), bo.G2_GEN)) == one, "bilinearity check failed"
+    assert fin(mill(g1(a), g2(b), z=0xdeadbeefcafe), mill(g1(bo.R - a * b % bo.R), bo.G2_GEN, z=12345)) == one, "Jacobian-P scaling failed"
     assert fin(mill(g1(a), g2(b)), mill(g1(bo.R - a * b % bo.R + 1), bo.G2_GEN)) != one, "non-degeneracy check failed"
 
 
