@@ -151,10 +151,20 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     const G1Aff* key_aff = registry ? static_cast<const G1Aff*>(s.reg_aff.p) : static_cast<const G1Aff*>(s.key_aff.p);
     const int32_t* key_code = registry ? static_cast<const int32_t*>(s.reg_code.p) : static_cast<const int32_t*>(s.key_code.p);
 
-    // ---- small arrays first (stream A), then signatures (stream B) and messages (stream C) are launched BEFORE the
-    //      wide per-key kernel so their few, long-running CTAs are already resident when it floods the SMs
+    // ---- small arrays + keys (stream A), then the wide per-key kernel is launched FIRST: its first wave puts one
+    //      57 344-register CTA on every SM, leaving room for exactly two 4 096-register CTAs of the signature /
+    //      message kernels (streams B, C, high priority), which therefore run under it without ever starving it
     B200_CUDA_TRY(cudaMemcpyAsync(d_small, s.stage.p, small_bytes, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
+    if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
+    B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
+    // ---- stream A: public keys
+    B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
+    if (!registry && n_keys) {
+        launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, static_cast<G1Aff*>(s.key_aff.p),
+                           static_cast<int32_t*>(s.key_code.p), sa);
+        e.launches++;
+    }
     B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
     B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
     if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
@@ -164,16 +174,6 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     e.launches += (T ? 1 : 0) + (n_msgs ? 2 : 0);
     B200_CUDA_TRY(cudaEventRecord(s.ev_b, sb));
     B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
-    if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
-    B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
-
-    // ---- stream A: public keys
-    B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
-    if (!registry && n_keys) {
-        launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, static_cast<G1Aff*>(s.key_aff.p),
-                           static_cast<int32_t*>(s.key_code.p), sa);
-        e.launches++;
-    }
     B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
     if (s.trace) cudaEventRecord(s.ev_t[0], sa);
     const uint32_t n_agg_tuples = (mode == MODE_FAST_AGGREGATE) ? T : 1;
