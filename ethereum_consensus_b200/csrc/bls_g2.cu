@@ -13,7 +13,10 @@
 namespace b200 {
 namespace {
 
-// 32-thread CTAs capped at 128 registers (4 096 per CTA): two of them fit beside a 57 344-register per-key CTA
+// Capped at 128 registers so that a 512-thread CTA fills one SM exactly (65 536 registers).  Strict mode launches these
+// latency-bound kernels as a few full-SM CTAs: measured on B200, small CTAs spread over all SMs lock the 57 344-register
+// CTAs of the per-key kernel out of every SM they touch (cost ~ their whole duration), whereas 32 dedicated SMs cost
+// the per-key kernel ~2 %.  Registry mode (no per-key kernel) spreads them as 32-thread CTAs for latency.
 __global__ void __maxnreg__(128) k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
                                                        int32_t* __restrict__ sig_code) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,15 +98,16 @@ __global__ void __launch_bounds__(32) k_g2_sum_compress(const G2Aff* __restrict_
 
 }  // namespace
 
-void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream) {
+void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, int threads, void* stream) {
     if (!n) return;
-    k_g2_sig_decode<<<(n + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
+    k_g2_sig_decode<<<(n + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
 }
-void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, void* stream) {
+void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, int threads,
+                       void* stream) {
     if (!n) return;
     G2Jac* tmp = static_cast<G2Jac*>(tmp_jac);
-    k_hash_to_g2_map<<<(2 * n + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, tmp);
-    k_hash_to_g2_finish<<<(n + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(tmp, n, out);
+    k_hash_to_g2_map<<<(2 * n + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, tmp);
+    k_hash_to_g2_finish<<<(n + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(tmp, n, out);
 }
 void launch_g2_sum_compress(const G2Aff* sigs, const int32_t* sig_code, uint32_t n, uint8_t* out96, int32_t* out_code, void* stream) {
     k_g2_sum_compress<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sigs, sig_code, n, out96, out_code);

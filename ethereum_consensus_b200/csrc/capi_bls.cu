@@ -18,7 +18,7 @@
 namespace b200 {
 
 struct BlsState {
-    cudaStream_t sb = nullptr, sc = nullptr;  // signatures / messages: high priority, run under the per-key kernel
+    cudaStream_t sb = nullptr, sc = nullptr;  // signatures / messages: run under the per-key kernel
     cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp;
     PinnedBuf stage;
@@ -30,6 +30,7 @@ struct BlsState {
     float last_dominant_ms = 0.f;
     bool trace = false;          // B200_BLS_TRACE=1: per-phase CUDA-event timings on stderr
     cudaEvent_t ev_t[8] = {nullptr};
+    int small_cta_strict = 512;  // B200_SMALL_CTA: CTA size of the signature / message kernels while K1 runs
     bool use_vm = true;  // lane-parallel pairing kernels (B200_PAIRING_VM=0 selects the one-thread-per-pair kernels)
 };
 
@@ -39,11 +40,16 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         if (const char* v = getenv("B200_G1_VARIANT")) set_g1_variant(atoi(v));
         if (const char* v = getenv("B200_PAIRING_VM")) s->use_vm = atoi(v) != 0;
         if (const char* v = getenv("B200_BLS_TRACE")) s->trace = atoi(v) != 0;
+        if (const char* v = getenv("B200_SMALL_CTA")) { int t = atoi(v); if (t >= 32 && t <= 512 && t % 32 == 0) s->small_cta_strict = t; }
         for (auto& ev : s->ev_t) B200_CUDA_TRY(cudaEventCreate(&ev));
-        int prio_lo = 0, prio_hi = 0;
-        B200_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sb, cudaStreamNonBlocking, prio_hi));
-        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sc, cudaStreamNonBlocking, prio_hi));
+        // High priority: the signature / message kernels are dispatched as soon as the per-key kernel's first wave
+        // retires (with equal priority they would only start on its last wave); in strict mode they are launched as
+        // full-SM CTAs so that they take ~32 SMs instead of touching all 148 (see bls_g2.cu).
+        int prio_lo = 0, prio = 0;
+        B200_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio));          // highest priority
+        if (const char* v = getenv("B200_SMALL_STREAM_PRIORITY")) prio = atoi(v);  // A/B knob
+        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sb, cudaStreamNonBlocking, prio));
+        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sc, cudaStreamNonBlocking, prio));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_c, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
@@ -153,7 +159,7 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
 
     // ---- small arrays + keys (stream A), then the wide per-key kernel is launched FIRST: its first wave puts one
     //      57 344-register CTA on every SM, leaving room for exactly two 4 096-register CTAs of the signature /
-    //      message kernels (streams B, C, high priority), which therefore run under it without ever starving it
+    //      message kernels (streams B, C), which therefore run under it without ever starving it
     B200_CUDA_TRY(cudaMemcpyAsync(d_small, s.stage.p, small_bytes, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
     if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
@@ -169,8 +175,9 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
     if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
     if (msg_bytes) B200_CUDA_TRY(cudaMemcpyAsync(s.msgs.p, msgs, msg_bytes, cudaMemcpyHostToDevice, sc));
-    launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), sb);
-    launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, s.h2c_tmp.p, sc);
+    const int small_threads = (!registry && n_keys >= 65536) ? s.small_cta_strict : 32;
+    launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), small_threads, sb);
+    launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, s.h2c_tmp.p, small_threads, sc);
     e.launches += (T ? 1 : 0) + (n_msgs ? 2 : 0);
     B200_CUDA_TRY(cudaEventRecord(s.ev_b, sb));
     B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
@@ -434,7 +441,7 @@ int32_t b200_aggregate(const uint8_t* sigs_flat, size_t n, uint8_t out[96]) {
     cudaStream_t sa = e.stream;
     B200_CUDA_TRY(cudaMemcpyAsync(s->sigs.p, sigs_flat, n * 96, cudaMemcpyHostToDevice, sa));
     launch_g2_sig_decode(static_cast<const uint8_t*>(s->sigs.p), uint32_t(n), static_cast<G2Aff*>(s->g2pts.p),
-                         static_cast<int32_t*>(s->sig_code.p), sa);
+                         static_cast<int32_t*>(s->sig_code.p), 32, sa);
     uint8_t* d_out = static_cast<uint8_t*>(s->out.p);
     launch_g2_sum_compress(static_cast<const G2Aff*>(s->g2pts.p), static_cast<const int32_t*>(s->sig_code.p), uint32_t(n),
                            d_out + 16, reinterpret_cast<int32_t*>(d_out), sa);
