@@ -30,6 +30,7 @@ struct BlsState {
     float last_dominant_ms = 0.f;
     bool trace = false;          // B200_BLS_TRACE=1: per-phase CUDA-event timings on stderr
     cudaEvent_t ev_t[8] = {nullptr};
+    int small_order = 0;         // B200_SMALL_ORDER: 0 co-run under K1, 1 run before K1 (serialised), 2 after K1
     int small_cta_strict = 512;  // B200_SMALL_CTA: CTA size of the signature / message kernels while K1 runs
     bool use_vm = true;  // lane-parallel pairing kernels (B200_PAIRING_VM=0 selects the one-thread-per-pair kernels)
 };
@@ -40,6 +41,7 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         if (const char* v = getenv("B200_G1_VARIANT")) set_g1_variant(atoi(v));
         if (const char* v = getenv("B200_PAIRING_VM")) s->use_vm = atoi(v) != 0;
         if (const char* v = getenv("B200_BLS_TRACE")) s->trace = atoi(v) != 0;
+        if (const char* v = getenv("B200_SMALL_ORDER")) s->small_order = atoi(v);
         if (const char* v = getenv("B200_SMALL_CTA")) { int t = atoi(v); if (t >= 32 && t <= 512 && t % 32 == 0) s->small_cta_strict = t; }
         for (auto& ev : s->ev_t) B200_CUDA_TRY(cudaEventCreate(&ev));
         // High priority: the signature / message kernels are dispatched as soon as the per-key kernel's first wave
@@ -164,23 +166,40 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
     if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
+    auto launch_small = [&]() -> int32_t {
+        const int small_threads = (!registry && n_keys >= 65536 && s.small_order == 0) ? s.small_cta_strict : 32;
+        B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
+        B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
+        if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
+        if (msg_bytes) B200_CUDA_TRY(cudaMemcpyAsync(s.msgs.p, msgs, msg_bytes, cudaMemcpyHostToDevice, sc));
+        launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), small_threads, sb);
+        launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, s.h2c_tmp.p, small_threads, sc);
+        e.launches += (T ? 1 : 0) + (n_msgs ? 2 : 0);
+        B200_CUDA_TRY(cudaEventRecord(s.ev_b, sb));
+        B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
+        return B200_SUCCESS;
+    };
+    const bool have_k1 = !registry && n_keys;
+    if (have_k1 && s.small_order == 1) {   // signatures / messages first, the per-key kernel only afterwards
+        int32_t rc = launch_small();
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_b, 0));
+        B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_c, 0));
+    }
     // ---- stream A: public keys
     B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
-    if (!registry && n_keys) {
+    if (have_k1) {
         launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, static_cast<G1Aff*>(s.key_aff.p),
                            static_cast<int32_t*>(s.key_code.p), sa);
         e.launches++;
     }
-    B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
-    B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
-    if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
-    if (msg_bytes) B200_CUDA_TRY(cudaMemcpyAsync(s.msgs.p, msgs, msg_bytes, cudaMemcpyHostToDevice, sc));
-    const int small_threads = (!registry && n_keys >= 65536) ? s.small_cta_strict : 32;
-    launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), small_threads, sb);
-    launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, s.h2c_tmp.p, small_threads, sc);
-    e.launches += (T ? 1 : 0) + (n_msgs ? 2 : 0);
-    B200_CUDA_TRY(cudaEventRecord(s.ev_b, sb));
-    B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
+    if (!(have_k1 && s.small_order == 1)) {
+        if (have_k1 && s.small_order == 2) {  // strictly after the per-key kernel
+            B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
+        }
+        int32_t rc = launch_small();
+        if (rc) return rc;
+    }
     B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
     if (s.trace) cudaEventRecord(s.ev_t[0], sa);
     const uint32_t n_agg_tuples = (mode == MODE_FAST_AGGREGATE) ? T : 1;

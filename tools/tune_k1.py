@@ -5,7 +5,7 @@ import numpy as np
 from ethereum_consensus_b200 import _lib, crypto, ssz, state as S
 L = C.CDLL('oracle/liboracle_bls.so')
 L.orc_pk_sequence.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p]
-nd = 4096
+nd = int(os.environ.get('TUNE_ND', '4096'))
 keys = np.empty((nd, 48), dtype=np.uint8)
 L.orc_pk_sequence((12345).to_bytes(32, 'big'), (987654321).to_bytes(32, 'big'), nd, keys.ctypes.data)
 reg = np.tile(keys, (1 << 21) // nd, 1) if False else np.tile(keys, ((1 << 21) // nd, 1))
