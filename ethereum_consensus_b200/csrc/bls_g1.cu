@@ -13,6 +13,9 @@
 #if defined(B200_G1_CALL_MUL)  // A/B knob: by-value function calls instead of inlined products in the per-key kernel
 #define B200_FP_MUL_CALL 1
 #endif
+// fp_pow's window table in dynamic shared memory (fp.cuh): every kernel here that can reach fp_pow is launched through
+// with_pow_tab() below.  Thread-local storage made the per-key kernel's speed depend on what else the process had run.
+#define B200_POW_TAB_SMEM 1
 #include <cuda_runtime.h>
 
 #include "bls_kernels.cuh"
@@ -167,33 +170,46 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
 
 // tuning knob (B200_G1_VARIANT): 0: 256 threads, 224 registers (default); threads x min CTAs/SM = 1: 128x2, 2: 128x3,
 // 3: 256x2, 4: 128x4, 5: 256x1 uncapped
+// dynamic shared memory for fp_pow's table; opts the kernel in to > 48 KiB once
+template <class K>
+static size_t with_pow_tab(K kernel, unsigned threads) {
+    const size_t bytes = fp_pow_smem_bytes(threads);
+    static const void* seen[16];  // kernels of equal signature share this instantiation: key by address
+    static int n_seen = 0;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (int i = 0; i < n_seen; i++) if (seen[i] == key) return bytes;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (n_seen < 16) seen[n_seen++] = key;
+    return bytes;
+}
 static int g_g1_variant = 0;
 void set_g1_variant(int v) { if (v >= 0 && v <= 5) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (g_g1_variant) {
-    case 1: k_g1_validate<128, 2><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
-    case 2: k_g1_validate<128, 3><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
-    case 3: k_g1_validate<256, 2><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
-    case 4: k_g1_validate<128, 4><<<(n + 127) / 128, 128, 0, st>>>(keys, n, out, codes); break;
-    case 5: k_g1_validate<256, 1><<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
-    default: k_g1_validate_main<<<(n + 255) / 256, 256, 0, st>>>(keys, n, out, codes); break;
+    case 1: k_g1_validate<128, 2><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 2>, 128), st>>>(keys, n, out, codes); break;
+    case 2: k_g1_validate<128, 3><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 3>, 128), st>>>(keys, n, out, codes); break;
+    case 3: k_g1_validate<256, 2><<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate<256, 2>, 256), st>>>(keys, n, out, codes); break;
+    case 4: k_g1_validate<128, 4><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 4>, 128), st>>>(keys, n, out, codes); break;
+    case 5: k_g1_validate<256, 1><<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate<256, 1>, 256), st>>>(keys, n, out, codes); break;
+    default: k_g1_validate_main<<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate_main, 256), st>>>(keys, n, out, codes); break;
     }
 }
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,
                          uint32_t n_tuples, G1Aff* agg, G1Pre* agg_pre, int32_t* pk_code, uint32_t* flags,
                          uint32_t extra_flags, void* stream) {
     if (!n_tuples) return;
-    k_g1_aggregate<<<(n_tuples + kAggWarps - 1) / kAggWarps, 32 * kAggWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+    k_g1_aggregate<<<(n_tuples + kAggWarps - 1) / kAggWarps, 32 * kAggWarps, with_pow_tab(k_g1_aggregate, 32 * kAggWarps),
+                     static_cast<cudaStream_t>(stream)>>>(
         keys, key_codes, index, off, n_tuples, agg, agg_pre, pk_code, flags, extra_flags);
 }
 void launch_g1_compress(const G1Aff* p, uint8_t* out48, void* stream) {
-    k_g1_compress<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p, out48);
+    k_g1_compress<<<1, 32, with_pow_tab(k_g1_compress, 32), static_cast<cudaStream_t>(stream)>>>(p, out48);
 }
 void launch_neg_g1(G1Aff* out, G1Pre* out_pre, void* stream) { k_neg_g1<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out, out_pre); }
 void launch_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch, void* stream) {
-    k_fp_selftest<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(n, seed, out_mismatch);
+    k_fp_selftest<<<(n + 127) / 128, 128, with_pow_tab(k_fp_selftest, 128), static_cast<cudaStream_t>(stream)>>>(n, seed, out_mismatch);
 }
 
 }  // namespace b200

@@ -256,17 +256,51 @@ static const uint32_t h_exp_p_minus_1_div_2[12] = B200_EXP_P_MINUS_1_DIV_2;
 
 // r = a^e, e given as 12 little-endian words; fixed 4-bit windows, left to right: ~380 squarings + ~95 table
 // products + 14 to build the table instead of ~190 products for plain square-and-multiply (the exponents used here —
-// (p+1)/4, (p-3)/4, p-2 — are dense).  The 16-entry table lives in thread-local memory (768 B, L1-resident).
-// `a` is public data: variable-time is fine.
-B200_BIG void fp_pow(Fp& r, const Fp& a, const uint32_t* e) {
-    Fp tab[16];
-    tab[0] = fp_one();
-    tab[1] = a;
-#pragma unroll 1
-    for (int i = 2; i < 16; i++) {
-        if (i & 1) fp_mul(tab[i], tab[i - 1], a); else fp_sqr(tab[i], tab[i >> 1]);
+// (p+1)/4, (p-3)/4, p-2 — are dense).  `a` is public data: variable-time is fine.
+//
+// Where the 15-entry table (720 B per thread) lives:
+//  * default: thread-local memory.  Its L1 residency depends on how the driver has laid out the context's local-memory
+//    pool, and that layout changes once ANY other CUDA module has launched a kernel in the process (measured: the
+//    per-key kernel goes 167 -> 197 ms, profiles/r1_tuning.md "foreign module effect").
+//  * B200_POW_TAB_SMEM (defined by a TU before including this header): dynamic shared memory, word-interleaved
+//    [(entry*12 + limb) * blockDim.x + threadIdx.x] so every access is bank-conflict-free.  Every kernel of that TU that
+//    reaches fp_pow must be launched with fp_pow_smem_bytes(threads) of dynamic shared memory.
+#if defined(__CUDA_ARCH__) && defined(B200_POW_TAB_SMEM)
+extern __shared__ uint32_t b200_pow_tab[];
+struct PowTab {
+    __device__ __forceinline__ void set(int i, const Fp& v) {
+        uint32_t* q = b200_pow_tab + (i - 1) * 12 * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 12; k++) q[k * blockDim.x] = v.l[k];
     }
-    Fp acc = fp_one();
+    __device__ __forceinline__ void get(Fp& v, int i) const {
+        const uint32_t* q = b200_pow_tab + (i - 1) * 12 * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 12; k++) v.l[k] = q[k * blockDim.x];
+    }
+};
+#else
+struct PowTab {
+    Fp t[15];
+    B200_HD void set(int i, const Fp& v) { t[i - 1] = v; }
+    B200_HD void get(Fp& v, int i) const { v = t[i - 1]; }
+};
+#endif
+constexpr size_t fp_pow_smem_bytes(unsigned threads) { return size_t(threads) * 15 * 12 * 4; }
+
+B200_BIG void fp_pow(Fp& r, const Fp& a, const uint32_t* e) {
+    PowTab tab;
+    tab.set(1, a);
+    {
+        Fp prev = a, cur, half;
+#pragma unroll 1
+        for (int i = 2; i < 16; i++) {
+            if (i & 1) fp_mul(cur, prev, a); else { tab.get(half, i >> 1); fp_sqr(cur, half); }
+            tab.set(i, cur);
+            prev = cur;
+        }
+    }
+    Fp acc = fp_one(), t;
     bool started = false;
 #pragma unroll 1
     for (int w = 11; w >= 0; w--) {
@@ -276,9 +310,9 @@ B200_BIG void fp_pow(Fp& r, const Fp& a, const uint32_t* e) {
             const uint32_t d = (word >> (4 * nib)) & 0xfu;
             if (started) {
                 fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc);
-                if (d) fp_mul(acc, acc, tab[d]);
+                if (d) { tab.get(t, d); fp_mul(acc, acc, t); }
             } else if (d) {
-                acc = tab[d];
+                tab.get(acc, d);
                 started = true;
             }
         }

@@ -13,6 +13,17 @@ if mode != "plain":
     torch.cuda.set_device(0)
     x = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     y = torch.ones(256 << 20, dtype=torch.uint8, device="cuda")
+    rt = C.CDLL([m.split()[-1] for m in open("/proc/self/maps") if "libcudart" in m][0])
+    a = torch.randn(4096, 4096, device="cuda", dtype=torch.bfloat16)
+    import threading, pynvml
+    pynvml.nvmlInit(); hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+    clk, sampling, allclk = [], [False], []
+    def sampler():
+        while True:
+            if sampling[0]:
+                clk.append(pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM))
+            time.sleep(0.002)
+    threading.Thread(target=sampler, daemon=True).start()
 _lib.init(0)
 ms = []
 for i in range(14):
@@ -28,5 +39,22 @@ for i in range(14):
         x.fill_(0x5a); torch.cuda.synchronize()
     elif mode == "small":          # 32 MiB write: smaller than L2
         x[:32 << 20].zero_(); torch.cuda.synchronize()
+    elif mode == "tiny":           # a 1 KiB foreign kernel
+        x[:1024].zero_(); torch.cuda.synchronize()
+    elif mode == "sleeponly":
+        time.sleep(0.05)
+    elif mode == "rtmemset":       # driver memset, no torch kernel
+        rt.cudaMemset(C.c_void_p(x.data_ptr()), 0, C.c_size_t(256 << 20)); rt.cudaDeviceSynchronize()
+    elif mode == "d2d":            # copy engine traffic only (no SM kernel)
+        rt.cudaMemcpy(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_size_t(256 << 20), 3); rt.cudaDeviceSynchronize()
+    elif mode == "sleep2":         # idle, then two runs back to back: does the second recover?
+        time.sleep(0.05); crypto.Registry(reg); ms.append(round(crypto.last_kernel_ms(), 1))
+    elif mode == "busy":           # keep the SMs busy right up to the call
+        for _ in range(40): torch.mm(a, a)
+    elif mode == "sleepclk":
+        time.sleep(0.05); clk.clear(); sampling[0] = True
     crypto.Registry(reg); ms.append(round(crypto.last_kernel_ms(), 1))
+    if mode == "sleepclk":
+        sampling[0] = False; allclk.append((min(clk), clk[:12]))
 print(mode, ms)
+if mode == "sleepclk": print(allclk[:4])
