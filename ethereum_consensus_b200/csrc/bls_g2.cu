@@ -13,11 +13,15 @@
 namespace b200 {
 namespace {
 
-// Capped at 128 registers so that a 512-thread CTA fills one SM exactly (65 536 registers).  Strict mode launches these
-// latency-bound kernels as a few full-SM CTAs: measured on B200, small CTAs spread over all SMs lock the 57 344-register
-// CTAs of the per-key kernel out of every SM they touch (cost ~ their whole duration), whereas 32 dedicated SMs cost
-// the per-key kernel ~2 %.  Registry mode (no per-key kernel) spreads them as 32-thread CTAs for latency.
-__global__ void __maxnreg__(128) k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
+// One warp per CTA: with only T items there is at most a warp or two per SM, so these kernels are latency-bound and
+// spread as 32-thread CTAs over every SM.  They run BEFORE the per-key kernel, not under it: measured on B200
+// (profiles/r1_tuning.md), any co-scheduling costs the per-key kernel more than these kernels take alone.
+// A/B on B200 (T=4096, both kernels together): 128-register cap + thread-local fp_pow table 14.4 ms; same cap with the
+// table in shared memory 16.7 ms; uncapped (234-255 registers) + shared table 24.4 ms — the by-value call ABI of this
+// TU saves/restores more registers around every product when the caller holds more of them.
+constexpr int kSmallCta = 32;
+#define B200_G2_BOUNDS __maxnreg__(128)
+__global__ void B200_G2_BOUNDS k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
                                                        int32_t* __restrict__ sig_code) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -37,7 +41,7 @@ __global__ void __maxnreg__(128) k_g2_sig_decode(const uint8_t* __restrict__ sig
 
 // hash_to_G2 in two launches: the two SSWU maps of a message are independent (2n threads), then one thread per message
 // adds them, clears the cofactor and normalises.
-__global__ void __maxnreg__(128) k_hash_to_g2_map(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ moff,
+__global__ void B200_G2_BOUNDS k_hash_to_g2_map(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ moff,
                                                         uint32_t n, G2Jac* __restrict__ tmp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
@@ -46,7 +50,7 @@ __global__ void __maxnreg__(128) k_hash_to_g2_map(const uint8_t* __restrict__ ms
     hash_to_g2_map(q, msgs + moff[m], size_t(moff[m + 1] - moff[m]), int(i & 1));
     tmp[i] = q;
 }
-__global__ void __maxnreg__(128) k_hash_to_g2_finish(const G2Jac* __restrict__ tmp, uint32_t n, G2Aff* __restrict__ out) {
+__global__ void B200_G2_BOUNDS k_hash_to_g2_finish(const G2Jac* __restrict__ tmp, uint32_t n, G2Aff* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const G2Jac q0 = tmp[2 * i], q1 = tmp[2 * i + 1];
@@ -98,19 +102,22 @@ __global__ void __launch_bounds__(32) k_g2_sum_compress(const G2Aff* __restrict_
 
 }  // namespace
 
-void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, int threads, void* stream) {
+constexpr size_t kPowTab = 0;  // thread-local table here (see above)
+
+void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream) {
     if (!n) return;
-    k_g2_sig_decode<<<(n + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
+    constexpr int threads = kSmallCta;
+    k_g2_sig_decode<<<(n + threads - 1) / threads, threads, kPowTab, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
 }
-void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, int threads,
-                       void* stream) {
+void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, void* stream) {
     if (!n) return;
+    constexpr int threads = kSmallCta;
     G2Jac* tmp = static_cast<G2Jac*>(tmp_jac);
-    k_hash_to_g2_map<<<(2 * n + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, tmp);
-    k_hash_to_g2_finish<<<(n + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(tmp, n, out);
+    k_hash_to_g2_map<<<(2 * n + threads - 1) / threads, threads, kPowTab, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, tmp);
+    k_hash_to_g2_finish<<<(n + threads - 1) / threads, threads, kPowTab, static_cast<cudaStream_t>(stream)>>>(tmp, n, out);
 }
 void launch_g2_sum_compress(const G2Aff* sigs, const int32_t* sig_code, uint32_t n, uint8_t* out96, int32_t* out_code, void* stream) {
-    k_g2_sum_compress<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sigs, sig_code, n, out96, out_code);
+    k_g2_sum_compress<<<1, 32, kPowTab, static_cast<cudaStream_t>(stream)>>>(sigs, sig_code, n, out96, out_code);
 }
 
 }  // namespace b200

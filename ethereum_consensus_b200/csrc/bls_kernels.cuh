@@ -32,11 +32,10 @@ void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint
                          uint32_t extra_flags, void* stream);
 // K3: decompress + subgroup-check every 96-byte signature
 //     `threads`: CTA size (32 = spread for latency, 512 = pack onto few SMs while the per-key kernel runs)
-void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, int threads, void* stream);
+void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream);
 // K4: hash_to_G2 of message i = bytes [moff[i], moff[i+1]) of `msgs`
 //     `tmp_jac`: scratch for 2n Jacobian G2 points (288 B each)
-void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, int threads,
-                       void* stream);
+void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, void* stream);
 // K5: one Miller loop per pair (g1[g1_idx[i]], g2[g2_idx[i]]); pairs whose tuple already failed are skipped
 void launch_miller(const G1Aff* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
                    const uint32_t* pair_tuple, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,

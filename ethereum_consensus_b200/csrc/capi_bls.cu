@@ -4,9 +4,10 @@
 // the kernels of bls_g1.cu / bls_g2.cu / bls_pairing.cu.  The host only stages bytes and index arrays.
 //
 // Flow for T tuples with NK public keys in total (strict mode):
-//   stream A: H2D keys,offsets | K1 key_validate (NK threads) | K2 per-tuple aggregate (T warps) ----+
-//   stream B: H2D sigs,msgs    | K3 sig decompress+subgroup (T) | K4 hash_to_G2 (T) ---------------+ |
-//   stream A: wait(B) | K5 Miller loops (2T threads) | K6 Gt product + final exponentiation (T) | D2H codes
+//   stream A: H2D offsets, keys (100 MB) ........ wait(B,C) | K1 key_validate (NK threads) | K2 per-tuple aggregate
+//   stream B: H2D sigs | K3 sig decompress + subgroup check (T threads)   } under the key copy, before K1
+//   stream C: H2D msgs | K4 hash_to_G2 (2T + T threads)                   }
+//   stream A: K5 Miller loops (2T teams of 8 lanes) | K6 Gt product + final exponentiation (T teams) | D2H codes
 // Registry mode skips K1: validated affine keys stay resident in HBM and K2 gathers them by validator index.
 #include <cstdlib>
 #include <cstring>
@@ -30,8 +31,10 @@ struct BlsState {
     float last_dominant_ms = 0.f;
     bool trace = false;          // B200_BLS_TRACE=1: per-phase CUDA-event timings on stderr
     cudaEvent_t ev_t[8] = {nullptr};
-    int small_order = 0;         // B200_SMALL_ORDER: 0 co-run under K1, 1 run before K1 (serialised), 2 after K1
-    int small_cta_strict = 512;  // B200_SMALL_CTA: CTA size of the signature / message kernels while K1 runs
+    // B200_SMALL_ORDER (A/B knob): where the signature / message kernels go relative to the per-key kernel K1.
+    // 1 (default) before it, 0 under it on high-priority streams, 2 after it.  Measured on B200 (T=4096, K=512):
+    // 199 / 211 / 201 ms per step — both compete for the same FMA-heavy pipe, so overlap buys nothing.
+    int small_order = 1;
     bool use_vm = true;  // lane-parallel pairing kernels (B200_PAIRING_VM=0 selects the one-thread-per-pair kernels)
 };
 
@@ -42,11 +45,8 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         if (const char* v = getenv("B200_PAIRING_VM")) s->use_vm = atoi(v) != 0;
         if (const char* v = getenv("B200_BLS_TRACE")) s->trace = atoi(v) != 0;
         if (const char* v = getenv("B200_SMALL_ORDER")) s->small_order = atoi(v);
-        if (const char* v = getenv("B200_SMALL_CTA")) { int t = atoi(v); if (t >= 32 && t <= 512 && t % 32 == 0) s->small_cta_strict = t; }
         for (auto& ev : s->ev_t) B200_CUDA_TRY(cudaEventCreate(&ev));
-        // High priority: the signature / message kernels are dispatched as soon as the per-key kernel's first wave
-        // retires (with equal priority they would only start on its last wave); in strict mode they are launched as
-        // full-SM CTAs so that they take ~32 SMs instead of touching all 148 (see bls_g2.cu).
+        // High priority only matters for B200_SMALL_ORDER=0 (dispatch under the per-key kernel as its CTAs retire).
         int prio_lo = 0, prio = 0;
         B200_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio));          // highest priority
         if (const char* v = getenv("B200_SMALL_STREAM_PRIORITY")) prio = atoi(v);  // A/B knob
@@ -159,21 +159,18 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
     const G1Aff* key_aff = registry ? static_cast<const G1Aff*>(s.reg_aff.p) : static_cast<const G1Aff*>(s.key_aff.p);
     const int32_t* key_code = registry ? static_cast<const int32_t*>(s.reg_code.p) : static_cast<const int32_t*>(s.key_code.p);
 
-    // ---- small arrays + keys (stream A), then the wide per-key kernel is launched FIRST: its first wave puts one
-    //      57 344-register CTA on every SM, leaving room for exactly two 4 096-register CTAs of the signature /
-    //      message kernels (streams B, C), which therefore run under it without ever starving it
+    // ---- small arrays + keys (stream A); signatures / messages on streams B, C (they overlap the 100 MB key copy)
     B200_CUDA_TRY(cudaMemcpyAsync(d_small, s.stage.p, small_bytes, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
     if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
     auto launch_small = [&]() -> int32_t {
-        const int small_threads = (!registry && n_keys >= 65536 && s.small_order == 0) ? s.small_cta_strict : 32;
         B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
         B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
         if (T) B200_CUDA_TRY(cudaMemcpyAsync(s.sigs.p, sigs, size_t(T) * 96, cudaMemcpyHostToDevice, sb));
         if (msg_bytes) B200_CUDA_TRY(cudaMemcpyAsync(s.msgs.p, msgs, msg_bytes, cudaMemcpyHostToDevice, sc));
-        launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), small_threads, sb);
-        launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, s.h2c_tmp.p, small_threads, sc);
+        launch_g2_sig_decode(static_cast<const uint8_t*>(s.sigs.p), T, d_g2 + n_msgs, static_cast<int32_t*>(s.sig_code.p), sb);
+        launch_hash_to_g2(static_cast<const uint8_t*>(s.msgs.p), d_small + o_moff, n_msgs, d_g2, s.h2c_tmp.p, sc);
         e.launches += (T ? 1 : 0) + (n_msgs ? 2 : 0);
         B200_CUDA_TRY(cudaEventRecord(s.ev_b, sb));
         B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
@@ -460,7 +457,7 @@ int32_t b200_aggregate(const uint8_t* sigs_flat, size_t n, uint8_t out[96]) {
     cudaStream_t sa = e.stream;
     B200_CUDA_TRY(cudaMemcpyAsync(s->sigs.p, sigs_flat, n * 96, cudaMemcpyHostToDevice, sa));
     launch_g2_sig_decode(static_cast<const uint8_t*>(s->sigs.p), uint32_t(n), static_cast<G2Aff*>(s->g2pts.p),
-                         static_cast<int32_t*>(s->sig_code.p), 32, sa);
+                         static_cast<int32_t*>(s->sig_code.p), sa);
     uint8_t* d_out = static_cast<uint8_t*>(s->out.p);
     launch_g2_sum_compress(static_cast<const G2Aff*>(s->g2pts.p), static_cast<const int32_t*>(s->sig_code.p), uint32_t(n),
                            d_out + 16, reinterpret_cast<int32_t*>(d_out), sa);
