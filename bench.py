@@ -136,6 +136,8 @@ def make_bls_workload(orc, T: int, K: int, rank: int, n_distinct: int = 1 << 15,
     kind[(u >= 0.02) & (u < 0.025)] = 3
     kind[(u >= 0.025) & (u < 0.0275)] = 4
     kind[(u >= 0.0275) & (u < 0.03)] = 5
+    if K < 2:
+        kind[kind == 5] = 1  # a cancelling pair needs two keys
     sks = np.empty((T, 32), dtype=np.uint8)
     for t in range(T):
         row = kd[t]
