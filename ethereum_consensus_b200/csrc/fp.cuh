@@ -254,68 +254,79 @@ static const uint32_t h_exp_p_minus_1_div_2[12] = B200_EXP_P_MINUS_1_DIV_2;
 #define B200_EXP_TABLE(name) h_##name
 #endif
 
-// r = a^e, e given as 12 little-endian words; fixed 4-bit windows, left to right: ~380 squarings + ~95 table
-// products + 14 to build the table instead of ~190 products for plain square-and-multiply (the exponents used here —
-// (p+1)/4, (p-3)/4, p-2 — are dense).  `a` is public data: variable-time is fine.
+// r = a^e, e given as 12 little-endian words.  Sliding 4-bit windows over a table of the 8 odd powers a, a^3 .. a^15:
+// for the dense 381-bit exponents used here ((p+1)/4, (p-3)/4, p-2) that is ~380 squarings + ~76 table products + 8 to
+// build the table (plain square-and-multiply: ~570; fixed 4-bit windows: ~490).  The exponent is the same constant for
+// every thread, so the window logic is uniform (no divergence).  `a` is public data: variable-time is fine.
 //
-// Where the 15-entry table (720 B per thread) lives:
+// Where the table (8 x 48 B per thread) lives:
 //  * default: thread-local memory.  Its L1 residency depends on how the driver has laid out the context's local-memory
 //    pool, and that layout changes once ANY other CUDA module has launched a kernel in the process (measured: the
-//    per-key kernel goes 167 -> 197 ms, profiles/r1_tuning.md "foreign module effect").
+//    per-key kernel went 167 -> 197 ms, profiles/r1_tuning.md "foreign module effect").
 //  * B200_POW_TAB_SMEM (defined by a TU before including this header): dynamic shared memory, word-interleaved
 //    [(entry*12 + limb) * blockDim.x + threadIdx.x] so every access is bank-conflict-free.  Every kernel of that TU that
 //    reaches fp_pow must be launched with fp_pow_smem_bytes(threads) of dynamic shared memory.
+constexpr int kPowTabEntries = 8;
 #if defined(__CUDA_ARCH__) && defined(B200_POW_TAB_SMEM)
 extern __shared__ uint32_t b200_pow_tab[];
 struct PowTab {
     __device__ __forceinline__ void set(int i, const Fp& v) {
-        uint32_t* q = b200_pow_tab + (i - 1) * 12 * blockDim.x + threadIdx.x;
+        uint32_t* q = b200_pow_tab + i * 12 * blockDim.x + threadIdx.x;
 #pragma unroll
         for (int k = 0; k < 12; k++) q[k * blockDim.x] = v.l[k];
     }
     __device__ __forceinline__ void get(Fp& v, int i) const {
-        const uint32_t* q = b200_pow_tab + (i - 1) * 12 * blockDim.x + threadIdx.x;
+        const uint32_t* q = b200_pow_tab + i * 12 * blockDim.x + threadIdx.x;
 #pragma unroll
         for (int k = 0; k < 12; k++) v.l[k] = q[k * blockDim.x];
     }
 };
 #else
 struct PowTab {
-    Fp t[15];
-    B200_HD void set(int i, const Fp& v) { t[i - 1] = v; }
-    B200_HD void get(Fp& v, int i) const { v = t[i - 1]; }
+    Fp t[kPowTabEntries];
+    B200_HD void set(int i, const Fp& v) { t[i] = v; }
+    B200_HD void get(Fp& v, int i) const { v = t[i]; }
 };
 #endif
-constexpr size_t fp_pow_smem_bytes(unsigned threads) { return size_t(threads) * 15 * 12 * 4; }
+constexpr size_t fp_pow_smem_bytes(unsigned threads) { return size_t(threads) * kPowTabEntries * 12 * 4; }
 
 B200_BIG void fp_pow(Fp& r, const Fp& a, const uint32_t* e) {
-    PowTab tab;
-    tab.set(1, a);
+    PowTab tab;  // tab[k] = a^(2k+1)
+    tab.set(0, a);
     {
-        Fp prev = a, cur, half;
+        Fp a2, cur = a;
+        fp_sqr(a2, a);
 #pragma unroll 1
-        for (int i = 2; i < 16; i++) {
-            if (i & 1) fp_mul(cur, prev, a); else { tab.get(half, i >> 1); fp_sqr(cur, half); }
-            tab.set(i, cur);
-            prev = cur;
-        }
+        for (int k = 1; k < kPowTabEntries; k++) { fp_mul(cur, cur, a2); tab.set(k, cur); }
     }
-    Fp acc = fp_one(), t;
+    int i = 383;
+    while (i >= 0 && !((e[i >> 5] >> (i & 31)) & 1u)) i--;
+    if (i < 0) { r = fp_one(); return; }
+    Fp acc, t;
     bool started = false;
 #pragma unroll 1
-    for (int w = 11; w >= 0; w--) {
-        const uint32_t word = e[w];
-#pragma unroll 1
-        for (int nib = 7; nib >= 0; nib--) {
-            const uint32_t d = (word >> (4 * nib)) & 0xfu;
-            if (started) {
-                fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc);
-                if (d) { tab.get(t, d); fp_mul(acc, acc, t); }
-            } else if (d) {
-                tab.get(acc, d);
-                started = true;
-            }
+    while (i >= 0) {
+        if (!((e[i >> 5] >> (i & 31)) & 1u)) {
+            fp_sqr(acc, acc);  // started is always true here: the scan begins at the top set bit
+            i--;
+            continue;
         }
+        int l = i + 1 < 4 ? i + 1 : 4;  // window = bits i .. i-l+1, then trimmed to end in a 1
+        const int lo = i - l + 1;
+        uint64_t two = e[lo >> 5];
+        if ((lo >> 5) + 1 < 12) two |= uint64_t(e[(lo >> 5) + 1]) << 32;
+        uint32_t w = uint32_t(two >> (lo & 31)) & ((1u << l) - 1u);
+        while (!(w & 1u)) { w >>= 1; l--; }
+        if (started) {
+#pragma unroll 1
+            for (int k = 0; k < l; k++) fp_sqr(acc, acc);
+            tab.get(t, int(w >> 1));
+            fp_mul(acc, acc, t);
+        } else {
+            tab.get(acc, int(w >> 1));
+            started = true;
+        }
+        i -= l;
     }
     r = acc;
 }
