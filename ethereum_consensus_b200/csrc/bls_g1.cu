@@ -173,8 +173,6 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
 
 }  // namespace
 
-// tuning knob (B200_G1_VARIANT): 0: 256 threads, 224 registers (default); threads x min CTAs/SM = 1: 128x2, 2: 128x3,
-// 3: 256x2, 4: 128x4, 5: 256x1 uncapped
 // dynamic shared memory for fp_pow's table; opts the kernel in to > 48 KiB once
 template <class K>
 static size_t with_pow_tab(K kernel, unsigned threads) {
@@ -187,7 +185,9 @@ static size_t with_pow_tab(K kernel, unsigned threads) {
     if (n_seen < 16) seen[n_seen++] = key;
     return bytes;
 }
-static int g_g1_variant = 0;
+// tuning knob (B200_G1_VARIANT): 7: 384 threads, 168 registers (default); 0: 256 threads, 224 registers;
+// threads x min CTAs/SM = 1: 128x2, 2: 128x3, 3: 256x2, 4: 128x4, 5: 256x1 uncapped
+static int g_g1_variant = 7;
 void set_g1_variant(int v) { if (v >= 0 && v <= 7) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;

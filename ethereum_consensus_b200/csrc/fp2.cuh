@@ -105,37 +105,48 @@ B200_HD bool fp_sqrt_and_inv(Fp& x, Fp& xinv, const Fp& d) {
     xinv = t;
     return fp_eq(chk, d);
 }
-// Square root in Fp2 by the complex method (norm to Fp, two Fp exponentiations instead of two Fp2 ones);
-// returns false if `a` is not a square.  Either root may be returned: callers fix the sign (sgn0 / flag bit).
+// Square root in Fp2 by the complex method: exactly two Fp exponentiations, no data-dependent retry (threads of a
+// warp stay converged).  Either root may be returned: callers fix the sign (sgn0 / flag bit).
+//
+// fp2_sqrt_real: a = a0 real.  a0 = s^2, or a0 = -s^2 = (s u)^2.
+B200_HD bool fp2_sqrt_real(Fp2& r, const Fp& a0) {
+    Fp s, c;
+    fp_pow(s, a0, B200_EXP_TABLE(exp_sqrt));   // s^2 = +-a0
+    fp_sqr(c, s);
+    if (fp_eq(c, a0)) { r.c0 = s; r.c1 = fp_zero(); } else { r.c0 = fp_zero(); r.c1 = s; }
+    return true;
+}
+// fp2_sqrt_with_norm_root: w with w.c1 != 0 and s = sqrt(norm(w)).  With d = (w0 + s)/2 and d' = (w0 - s)/2,
+// d d' = -w1^2/4, so exactly one of them is a residue, and ONE exponentiation t = d^((p-3)/4), x = d t serves both:
+//   x^2 =  d: root = (x, w1 t / 2)            (1/x = t)
+//   x^2 = -d: root = (-w1 t / 2, x)           (1/x = -t; (-w1 t/2)^2 = -w1^2/(4 d) = d')
+B200_BIG bool fp2_sqrt_with_norm_root(Fp2& r, const Fp2& w, const Fp& s) {
+    Fp d, t, x, chk, h;
+    fp_add(d, w.c0, s);
+    fp_half(d, d);
+    fp_pow(t, d, B200_EXP_TABLE(exp_p_minus_3_div_4));
+    fp_mul(x, d, t);
+    fp_sqr(chk, x);
+    fp_mul(h, w.c1, t);
+    fp_half(h, h);
+    Fp2 cand;
+    if (fp_eq(chk, d)) { cand.c0 = x; cand.c1 = h; } else { fp_neg(cand.c0, h); cand.c1 = x; }
+    Fp2 sq;
+    fp2_sqr(sq, cand);
+    r = cand;
+    return fp2_eq(sq, w);
+}
+// returns false if `a` is not a square
 B200_BIG bool fp2_sqrt(Fp2& r, const Fp2& a) {
-    if (fp2_is_zero(a)) { r = a; return true; }
-    Fp2 x;
-    if (fp_is_zero(a.c1)) {
-        Fp s;
-        if (fp_sqrt(s, a.c0)) { x.c0 = s; x.c1 = fp_zero(); }
-        else { Fp n; fp_neg(n, a.c0); fp_sqrt(s, n); x.c0 = fp_zero(); x.c1 = s; }  // (s u)^2 = -s^2 = a0
-    } else {
-        Fp n, t, s, d, x0, x0inv;
-        fp_sqr(n, a.c0);
-        fp_sqr(t, a.c1);
-        fp_add(n, n, t);                       // norm
-        if (!fp_sqrt(s, n)) return false;      // a square in Fp2 has a square norm
-        fp_add(d, a.c0, s);
-        fp_half(d, d);                         // (a0 + s)/2
-        bool ok = !fp_is_zero(d) && fp_sqrt_and_inv(x0, x0inv, d);
-        if (!ok) {
-            fp_sub(d, a.c0, s);
-            fp_half(d, d);                     // (a0 - s)/2
-            if (fp_is_zero(d) || !fp_sqrt_and_inv(x0, x0inv, d)) return false;
-        }
-        fp_mul(t, a.c1, x0inv);
-        fp_half(t, t);                         // x1 = a1 / (2 x0)
-        x.c0 = x0; x.c1 = t;
-    }
-    Fp2 chk;
-    fp2_sqr(chk, x);
-    r = x;
-    return fp2_eq(chk, a);
+    if (fp_is_zero(a.c1)) return fp2_sqrt_real(r, a.c0);
+    Fp n, t, s, c;
+    fp_sqr(n, a.c0);
+    fp_sqr(t, a.c1);
+    fp_add(n, n, t);                           // norm; a is a square in Fp2 iff its norm is one in Fp
+    fp_pow(s, n, B200_EXP_TABLE(exp_sqrt));
+    fp_sqr(c, s);
+    if (!fp_eq(c, n)) return false;
+    return fp2_sqrt_with_norm_root(r, a, s);
 }
 // RFC 9380 sgn0 (m = 2)
 B200_HD uint32_t fp2_sgn0(const Fp2& a) {

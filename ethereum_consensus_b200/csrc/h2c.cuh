@@ -90,12 +90,33 @@ B200_BIG void sswu_map(Fp2& x, Fp2& y, const Fp2& t) {
         fp2_mul(x1, c, inv);
     }
     sswu_g(gx, x1);
-    if (fp2_sqrt(yy, gx)) {
+    // y = sqrt(g(x1)) if that is a square, else x = Z t^2 x1 and y = sqrt(g(x)) = t^3 sqrt(Z^3 g(x1)).  One shared
+    // exponentiation s = norm(g(x1))^((p+1)/4) decides which: s^2 = norm (square) or s^2 = -norm, and then
+    // s * sqrt(-norm(Z^3)) is the root of norm(Z^3 g(x1)).  A second one finishes the complex-method root: two
+    // exponentiations per map and no divergent retry.
+    Fp n, tt, s, c;
+    fp_sqr(n, gx.c0);
+    fp_sqr(tt, gx.c1);
+    fp_add(n, n, tt);
+    fp_pow(s, n, B200_EXP_TABLE(exp_sqrt));
+    fp_sqr(c, s);
+    const bool is_sq = fp_eq(c, n);
+    Fp2 w = gx;
+    if (!is_sq) {
+        const Fp2 z3 = B200_FP2_SSWU_Z3;
+        const Fp cs = B200_FP_SSWU_SQRT_NEG_NORM_Z3;
+        fp2_mul(w, z3, gx);
+        fp_mul(s, s, cs);
+    }
+    bool ok = !fp_is_zero(w.c1) && fp2_sqrt_with_norm_root(yy, w, s);
+    if (!ok) fp2_sqrt(yy, w);      // real w (probability ~2^-381): the general routine
+    if (is_sq) {
         x = x1;
     } else {
+        Fp2 t3;
         fp2_mul(x, zt2, x1);
-        sswu_g(gx, x);
-        fp2_sqrt(yy, gx);          // always a square here
+        fp2_mul(t3, t2, t);
+        fp2_mul(yy, yy, t3);
     }
     if (fp2_sgn0(t) != fp2_sgn0(yy)) fp2_neg(yy, yy);
     y = yy;

@@ -88,12 +88,28 @@ def test_host_math_fields_match_oracle(host_math):
         host_math.hm_fp2_op(2, enc(a), enc(b), out); assert dec(out) == bo.f2_inv(a)
         ok = host_math.hm_fp2_op(3, enc(a), enc(b), out); assert bool(ok) == (bo.f2_sqrt(a) is not None)
         assert host_math.hm_fp2_op(4, enc(a), enc(b), out) == bo.f2_sgn0(a)
+    # complex-method square root (two exponentiations, shared between the residue / non-residue sub-cases): every
+    # sub-case of fp2_sqrt_with_norm_root and the real-input path, checked by squaring
+    qr = next(x for x in range(2, 50) if pow(x, (bo.P - 1) // 2, bo.P) == 1)
+    nqr = next(x for x in range(2, 50) if pow(x, (bo.P - 1) // 2, bo.P) == bo.P - 1)
+    cases = [(0, 0), (qr, 0), (nqr, 0), (0, qr), (0, nqr), (bo.P - 1, 0), (1, 0)]
+    cases += [bo.f2_sqr((rnd.randrange(bo.P), rnd.randrange(bo.P))) for _ in range(40)]
+    cases += [(rnd.randrange(bo.P), rnd.randrange(bo.P)) for _ in range(40)]
+    n_sq = 0
+    for a in cases:
+        ok = host_math.hm_fp2_op(3, enc(a), enc(a), out)
+        assert bool(ok) == (bo.f2_sqrt(a) is not None), a
+        if ok:
+            n_sq += 1
+            assert bo.f2_sqr(dec(out)) == (a[0] % bo.P, a[1] % bo.P)
+    assert 45 < n_sq < len(cases)
     assert host_math.hm_fp12_selftest() == 63
 
 
 def test_host_math_hash_to_g2_matches_oracle(host_math):
     o = C.create_string_buffer(192); inf = C.c_int()
-    for m in (b"", b"abc", B2_MSG, bytes(32), bytes(range(100)), bytes(255)):
+    import hashlib
+    for m in [b"", b"abc", B2_MSG, bytes(32), bytes(range(100)), bytes(255)] + [hashlib.sha256(b"h2c%d" % i).digest() for i in range(24)]:
         host_math.hm_hash_to_g2(m, len(m), o, C.byref(inf))
         pt = ((int.from_bytes(o.raw[0:48], "big"), int.from_bytes(o.raw[48:96], "big")),
               (int.from_bytes(o.raw[96:144], "big"), int.from_bytes(o.raw[144:], "big")))
