@@ -1,4 +1,5 @@
 // extern "C" entry points — engine life cycle and the SSZ half of include/b200_consensus.h.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -54,7 +55,7 @@ int32_t check_ready(Engine& e) {
 }
 
 int32_t run_oneshot(Engine& e, SszPlan& plan, const std::vector<uint32_t>& outputs, uint8_t* out) {
-    return plan.run(e, e.arena, e.fields, e.planbuf, false, outputs, out);
+    return plan.run(e, e.arena, e.fields, e.planbuf, COPY_ALL, outputs, out);
 }
 
 }  // namespace
@@ -65,9 +66,29 @@ using namespace b200;
 struct b200_state {
     SszPlan plan;
     std::vector<uint32_t> outputs;
-    DevBuf arena, fields, planbuf;
+    DevBuf arena, fields, planbuf, selbuf, scatter;
     bool uploaded = false;
+    // ---- incremental re-hash (b200_state_update_* / b200_state_root_incremental) ----
+    // Host shadow of the serialization with everything EXCEPT the five big lists filled in (their byte ranges stay
+    // untouched zero pages of an anonymous mapping): small-field updates patch it and the plan is rebuilt from it.
+    uint8_t* shadow = nullptr;
+    size_t len = 0;
+    int preset = 0;
+    StateOffsets so;
+    std::vector<uint32_t> dirty[5];  // per big list: changed first-job inputs (records / 32-byte chunks), unsorted
+    bool small_dirty = false;
+    ~b200_state() { free(shadow); }
 };
+
+namespace {
+constexpr int kBigVar[5] = {2, 3, 4, 5, 6};         // StateOffsets::var index of each big list
+constexpr uint32_t kBigElem[5] = {121, 8, 1, 1, 8};  // element size in bytes
+// first-job input covering element i of big list f: a Validator record, or the 32-byte chunk of a packed list
+inline uint32_t big_input_of(int f, uint64_t i) { return uint32_t(f == 0 ? i : (i * kBigElem[f]) / 32); }
+inline uint64_t big_count(const b200_state* h, int f) {
+    return uint64_t(h->so.var[kBigVar[f] + 1] - h->so.var[kBigVar[f]]) / kBigElem[f];
+}
+}  // namespace
 
 extern "C" {
 
@@ -234,11 +255,24 @@ int32_t b200_state_upload_deneb(const uint8_t* ssz, size_t len, int32_t preset, 
     if (rc) return rc;
     if (!ssz || !out_handle) return B200_ERR_BAD_ARG;
     std::unique_ptr<b200_state> h(new b200_state());
-    rc = build_beacon_state_plan(h->plan, ssz, len, preset, h->outputs);
-    if (rc) { e.last_error = "malformed deneb BeaconState SSZ"; return rc; }
-    uint8_t root[32];
-    rc = h->plan.run(e, h->arena, h->fields, h->planbuf, false, h->outputs, root);  // uploads + first hash
-    if (rc) { h->arena.release(); h->fields.release(); h->planbuf.release(); return rc; }
+    {
+        SszPlan first;  // reads the caller's buffer
+        std::vector<uint32_t> outs;
+        rc = build_beacon_state_plan(first, ssz, len, preset, outs);
+        if (rc) { e.last_error = "malformed deneb BeaconState SSZ"; return rc; }
+        uint8_t root[32];
+        rc = first.run(e, h->arena, h->fields, h->planbuf, COPY_ALL, outs, root);  // uploads + first hash
+        if (rc) { h->arena.release(); h->fields.release(); h->planbuf.release(); return rc; }
+    }
+    // keep what is needed to re-plan without the caller's buffer: the serialization minus the big lists
+    if (!parse_beacon_state(ssz, len, preset, h->so)) return B200_ERR_SSZ_MALFORMED;
+    h->len = len; h->preset = preset;
+    h->shadow = static_cast<uint8_t*>(calloc(len ? len : 1, 1));
+    if (!h->shadow) { e.last_error = "out of host memory for the state shadow"; return B200_ERR_CUDA; }
+    memcpy(h->shadow, ssz, h->so.var[2]);
+    memcpy(h->shadow + h->so.var[7], ssz + h->so.var[7], len - h->so.var[7]);
+    rc = build_beacon_state_plan(h->plan, h->shadow, len, preset, h->outputs);  // same layout: it depends on lengths only
+    if (rc) return rc;
     h->uploaded = true;
     *out_handle = h.release();
     return B200_SUCCESS;
@@ -250,7 +284,7 @@ int32_t b200_state_root(b200_state* h, uint8_t out[32]) {
     int32_t rc = check_ready(e);
     if (rc) return rc;
     if (!h || !h->uploaded || !out) return B200_ERR_BAD_ARG;
-    return h->plan.run(e, h->arena, h->fields, h->planbuf, true, h->outputs, out);
+    return h->plan.run(e, h->arena, h->fields, h->planbuf, COPY_NONE, h->outputs, out);
 }
 
 void b200_state_free(b200_state* h) {
@@ -258,8 +292,124 @@ void b200_state_free(b200_state* h) {
     Engine& e = engine();
     Guard g(e);
     if (e.ready) { cudaSetDevice(e.device); cudaStreamSynchronize(e.stream); }
-    h->arena.release(); h->fields.release(); h->planbuf.release();
+    h->arena.release(); h->fields.release(); h->planbuf.release(); h->selbuf.release(); h->scatter.release();
     delete h;
+}
+
+int32_t b200_state_update_elements(b200_state* h, int32_t field, const uint64_t* indices, const uint8_t* values, size_t n) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!h || !h->uploaded || field < 0 || field > 4 || (n && (!indices || !values)) || n > 0xffffffffull) return B200_ERR_BAD_ARG;
+    if (!n) return B200_SUCCESS;
+    const uint64_t count = big_count(h, field);
+    for (size_t i = 0; i < n; i++)
+        if (indices[i] >= count) { e.last_error = "state_update_elements: index beyond the list length"; return B200_ERR_BAD_ARG; }
+    uint64_t field_off = 0; size_t nbytes = 0;
+    if (!h->plan.chain_field(field, &field_off, &nbytes)) return B200_ERR_BAD_ARG;
+    const uint32_t elem = kBigElem[field];
+    // [indices | values] through pinned staging, then a scatter kernel into the resident list
+    const size_t off_vals = n * 8;
+    const size_t total = off_vals + n * elem;
+    B200_CUDA_TRY(e.staging.reserve(total));
+    B200_CUDA_TRY(h->scatter.reserve(total));
+    memcpy(e.staging.p, indices, n * 8);
+    memcpy(static_cast<uint8_t*>(e.staging.p) + off_vals, values, n * elem);
+    B200_CUDA_TRY(cudaMemcpyAsync(h->scatter.p, e.staging.p, total, cudaMemcpyHostToDevice, e.stream));
+    launch_scatter(static_cast<uint8_t*>(h->fields.p) + field_off, static_cast<const uint64_t*>(h->scatter.p),
+                   static_cast<const uint8_t*>(h->scatter.p) + off_vals, uint32_t(n), elem, e.stream);
+    e.launches++;
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    for (size_t i = 0; i < n; i++) h->dirty[field].push_back(big_input_of(field, indices[i]));
+    return B200_SUCCESS;
+}
+
+int32_t b200_state_update_bytes(b200_state* h, uint64_t ssz_offset, const uint8_t* data, size_t n) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!h || !h->uploaded || (n && !data) || ssz_offset > h->len || n > h->len - ssz_offset) return B200_ERR_BAD_ARG;
+    if (!n) return B200_SUCCESS;
+    const uint64_t lo = ssz_offset, hi = ssz_offset + n;
+    // (1) the parts outside the big lists: patch the shadow; the variable-size offsets must not change
+    std::vector<uint8_t> saved;
+    auto patch_small = [&](uint64_t a, uint64_t b) {  // [a, b) is a small region of the serialization
+        const uint64_t x = std::max(a, lo), y = std::min(b, hi);
+        if (x >= y) return;
+        saved.insert(saved.end(), h->shadow + x, h->shadow + y);
+        memcpy(h->shadow + x, data + (x - lo), y - x);
+    };
+    auto restore_small = [&](uint64_t a, uint64_t b, size_t& pos) {
+        const uint64_t x = std::max(a, lo), y = std::min(b, hi);
+        if (x >= y) return;
+        memcpy(h->shadow + x, saved.data() + pos, y - x);
+        pos += y - x;
+    };
+    patch_small(0, h->so.var[2]);
+    patch_small(h->so.var[7], h->len);
+    if (!saved.empty()) {
+        StateOffsets so2;
+        bool ok = parse_beacon_state(h->shadow, h->len, h->preset, so2);
+        for (int i = 0; ok && i < 10; i++) ok = so2.var[i] == h->so.var[i];
+        if (!ok) {  // would move or resize a variable-size field: not an in-place update
+            size_t pos = 0;
+            restore_small(0, h->so.var[2], pos);
+            restore_small(h->so.var[7], h->len, pos);
+            e.last_error = "state_update_bytes: the update changes a variable-size field's offset or length; re-upload instead";
+            return B200_ERR_BAD_ARG;
+        }
+        h->small_dirty = true;
+    }
+    // (2) the parts inside big lists: copy into the resident list, mark the covered inputs dirty
+    for (int f = 0; f < 5; f++) {
+        const uint64_t a = h->so.var[kBigVar[f]], b = h->so.var[kBigVar[f] + 1];
+        const uint64_t x = std::max(a, lo), y = std::min(b, hi);
+        if (x >= y) continue;
+        uint64_t field_off = 0; size_t nbytes = 0;
+        if (!h->plan.chain_field(f, &field_off, &nbytes)) return B200_ERR_BAD_ARG;
+        B200_CUDA_TRY(e.staging.reserve(y - x));
+        memcpy(e.staging.p, data + (x - lo), y - x);
+        B200_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(h->fields.p) + field_off + (x - a), e.staging.p, y - x,
+                                      cudaMemcpyHostToDevice, e.stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+        const uint32_t unit = f == 0 ? 121u : 32u;
+        for (uint64_t u = (x - a) / unit; u <= (y - 1 - a) / unit; u++) h->dirty[f].push_back(uint32_t(u));
+    }
+    return B200_SUCCESS;
+}
+
+int32_t b200_state_root_incremental(b200_state* h, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!h || !h->uploaded || !out) return B200_ERR_BAD_ARG;
+    if (h->small_dirty) {  // re-plan from the shadow: same arena / field layout, fresh small leaves
+        SszPlan np;
+        std::vector<uint32_t> outs;
+        rc = build_beacon_state_plan(np, h->shadow, h->len, h->preset, outs);
+        if (rc) return rc;
+        if (np.arena_nodes() != h->plan.arena_nodes() || np.field_bytes() != h->plan.field_bytes() || outs != h->outputs) {
+            e.last_error = "state_root_incremental: plan layout changed";
+            return B200_ERR_BAD_ARG;
+        }
+        h->plan = std::move(np);
+    }
+    std::vector<std::vector<uint32_t>> dirty(h->plan.n_chains());
+    for (int f = 0; f < 5 && size_t(f) < dirty.size(); f++) {
+        dirty[size_t(f)] = h->dirty[f];
+        std::sort(dirty[size_t(f)].begin(), dirty[size_t(f)].end());
+        dirty[size_t(f)].erase(std::unique(dirty[size_t(f)].begin(), dirty[size_t(f)].end()), dirty[size_t(f)].end());
+    }
+    rc = h->plan.run(e, h->arena, h->fields, h->planbuf, h->small_dirty ? COPY_SMALL_ONLY : COPY_NONE, h->outputs, out,
+                     &dirty, &h->selbuf);
+    if (rc) return rc;
+    for (auto& d : h->dirty) d.clear();
+    h->small_dirty = false;
+    return B200_SUCCESS;
 }
 
 int32_t b200_htr_beacon_state_deneb_shard(const uint8_t* ssz, size_t len, int32_t preset, int32_t rank, int32_t world,

@@ -69,22 +69,9 @@ __device__ __forceinline__ uint32_t smem_be_word(const uint32_t* sm, uint32_t of
     return __byte_perm(lo, hi, sel);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(kStageThreads, MINB) k_validator_roots(const __grid_constant__ Job jb) {
-    __shared__ __align__(16) uint32_t smem[(kStageThreads * 121 + 16) / 4 + 4];
-    const uint32_t blk = blockIdx.x;
-    // stage 256 x 121 B (30 976 B, a multiple of 16) with coalesced 16-byte loads
-    const uint64_t first = uint64_t(blk) * kStageThreads;
-    const uint64_t nrec = min(uint64_t(kStageThreads), jb.n_in - first);
-    const uint32_t nbytes = uint32_t(nrec) * 121u;
-    const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(jb.src) + first * 121u);
-    uint4* s4 = reinterpret_cast<uint4*>(smem);
-    const uint32_t nvec = (nbytes + 15) >> 4;  // the field buffer is padded to a 16-byte multiple
-    for (uint32_t i = threadIdx.x; i < nvec; i += kStageThreads) s4[i] = g[i];
-    __syncthreads();
-    if (threadIdx.x >= nrec) return;
-    const uint32_t base = threadIdx.x * 121u;
-    uint32_t m[16], x[8], y[8], ab[8], root[8];
+// hash_tree_root(Validator) of the 121-byte record staged at byte offset `base` of `smem`
+__device__ __forceinline__ void validator_root(const uint32_t* smem, uint32_t base, uint32_t root[8]) {
+    uint32_t m[16], x[8], y[8], ab[8];
     // pubkey: 48 bytes -> 2 chunks -> 1 hash
 #pragma unroll
     for (int i = 0; i < 12; i++) m[i] = smem_be_word(smem, base + 4 * i);
@@ -115,6 +102,24 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_validator_roots(const _
     sha256_msg64(m, y);
     hash_pair_words(x, y, x);
     hash_pair_words(ab, x, root);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kStageThreads, MINB) k_validator_roots(const __grid_constant__ Job jb) {
+    __shared__ __align__(16) uint32_t smem[(kStageThreads * 121 + 16) / 4 + 4];
+    const uint32_t blk = blockIdx.x;
+    // stage 256 x 121 B (30 976 B, a multiple of 16) with coalesced 16-byte loads
+    const uint64_t first = uint64_t(blk) * kStageThreads;
+    const uint64_t nrec = min(uint64_t(kStageThreads), jb.n_in - first);
+    const uint32_t nbytes = uint32_t(nrec) * 121u;
+    const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(jb.src) + first * 121u);
+    uint4* s4 = reinterpret_cast<uint4*>(smem);
+    const uint32_t nvec = (nbytes + 15) >> 4;  // the field buffer is padded to a 16-byte multiple
+    for (uint32_t i = threadIdx.x; i < nvec; i += kStageThreads) s4[i] = g[i];
+    __syncthreads();
+    if (threadIdx.x >= nrec) return;
+    uint32_t root[8];
+    validator_root(smem, threadIdx.x * 121u, root);
     store_node(jb.dst + (first + threadIdx.x) * 8, root);
 }
 
@@ -186,6 +191,49 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_merkle_stage(const __gr
     }
 }
 
+
+// ---- dirty-path variants (incremental re-hash of a device-resident state) --------------------
+// Same per-thread work as the dense kernels, but thread t handles output sel[t] of the job instead of output t.
+__global__ void __launch_bounds__(kStageThreads) k_validator_roots_sparse(const __grid_constant__ Job jb,
+                                                                          const uint32_t* __restrict__ sel, uint32_t n_sel) {
+    __shared__ __align__(16) uint32_t smem[(kStageThreads * 121 + 16) / 4 + 4];
+    const uint32_t t = blockIdx.x * kStageThreads + threadIdx.x;
+    if (t >= n_sel) return;
+    const uint32_t rec = sel[t];
+    const uint8_t* g = reinterpret_cast<const uint8_t*>(jb.src) + uint64_t(rec) * 121u;
+    uint8_t* sb = reinterpret_cast<uint8_t*>(smem) + threadIdx.x * 121u;
+    for (int i = 0; i < 121; i++) sb[i] = g[i];  // each thread stages (and later reads) only its own record
+    // (smem_be_word loads whole words, so it touches neighbouring records' bytes, but only selects this record's)
+    __syncwarp();
+    uint32_t root[8];
+    validator_root(smem, threadIdx.x * 121u, root);
+    store_node(jb.dst + uint64_t(rec) * 8, root);
+}
+__global__ void __launch_bounds__(kStageThreads) k_merkle_reduce_sparse(const __grid_constant__ Job jb,
+                                                                        const uint32_t* __restrict__ zero_nodes,
+                                                                        const uint32_t* __restrict__ sel, uint32_t n_sel) {
+    const uint32_t t = blockIdx.x * kStageThreads + threadIdx.x;
+    if (t >= n_sel) return;
+    const uint64_t o = sel[t];
+    uint32_t out[8];
+    switch (jb.nlev) {
+    case 0: subtree<0>(jb, zero_nodes, o, out); break;
+    case 1: subtree<1>(jb, zero_nodes, o << 1, out); break;
+    case 2: subtree<2>(jb, zero_nodes, o << 2, out); break;
+    default: subtree<3>(jb, zero_nodes, o << 3, out); break;
+    }
+    store_node(jb.dst + o * 8, out);
+}
+// dst[idx[i] * elem .. +elem) = vals[i * elem .. +elem)   (elem in {1, 8, 121}: byte copies, any alignment)
+__global__ void k_scatter_elements(uint8_t* __restrict__ dst, const uint64_t* __restrict__ idx, const uint8_t* __restrict__ vals,
+                                   uint32_t n, uint32_t elem) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint8_t* d = dst + idx[t] * elem;
+    const uint8_t* v = vals + uint64_t(t) * elem;
+    for (uint32_t i = 0; i < elem; i++) d[i] = v[i];
+}
+
 // Single-CTA finisher: executes the planner's op list wave by wave (all ops of a wave are independent).
 __global__ void __launch_bounds__(kFinisherThreads) k_merkle_finisher(uint32_t* arena, const FinOp* ops,
                                                                         const uint32_t* wave_end, int nwaves) {
@@ -236,6 +284,18 @@ void launch_stage(const StageDesc& sd, void* stream) {
     case 4: k_merkle_stage<4><<<sd.nblocks, kStageThreads, 0, st>>>(sd); break;
     default: k_merkle_stage<3><<<sd.nblocks, kStageThreads, 0, st>>>(sd); break;
     }
+}
+
+void launch_sparse(const Job& jb, const uint32_t* zero_nodes, const uint32_t* sel, uint32_t n_sel, void* stream) {
+    if (!n_sel) return;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t nb = (n_sel + kStageThreads - 1) / kStageThreads;
+    if (jb.type == JOB_VALIDATORS) k_validator_roots_sparse<<<nb, kStageThreads, 0, st>>>(jb, sel, n_sel);
+    else k_merkle_reduce_sparse<<<nb, kStageThreads, 0, st>>>(jb, zero_nodes, sel, n_sel);
+}
+void launch_scatter(uint8_t* dst, const uint64_t* idx, const uint8_t* vals, uint32_t n, uint32_t elem, void* stream) {
+    if (!n) return;
+    k_scatter_elements<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, idx, vals, n, elem);
 }
 
 void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream) {

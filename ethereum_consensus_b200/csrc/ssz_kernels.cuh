@@ -45,6 +45,9 @@ constexpr int kMaxWaves = 256;
 void set_ssz_tuning(int minb_validators, int minb_stage);
 void launch_validators(const Job& jb, void* stream);
 void launch_stage(const StageDesc& sd, void* stream);
+// dirty-path variants: thread t handles output sel[t] (JOB_VALIDATORS or JOB_REDUCE only)
+void launch_sparse(const Job& jb, const uint32_t* zero_nodes, const uint32_t* sel, uint32_t n_sel, void* stream);
+void launch_scatter(uint8_t* dst, const uint64_t* idx, const uint8_t* vals, uint32_t n, uint32_t elem, void* stream);
 void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream);
 
 }  // namespace b200

@@ -64,12 +64,23 @@ uint64_t SszPlan::stage_field(const uint8_t* src, size_t nbytes) {
     uint64_t off = (field_next_ + 255) & ~uint64_t(255);
     size_t padded = ((nbytes + 31) & ~size_t(31)) + 32;
     field_next_ = off + padded;
-    if (nbytes) copies_.push_back(HostCopy{src, nbytes, off, padded - nbytes, false});
+    if (nbytes) {
+        copies_.push_back(HostCopy{src, nbytes, off, padded - nbytes, false, cur_chain_});
+        if (cur_chain_ >= 0) chains_[size_t(cur_chain_)].copy = int(copies_.size()) - 1;
+    }
     return off;
 }
 void SszPlan::add_job(size_t stage, const PJob& j) {
     if (stages_.size() <= stage) stages_.resize(stage + 1);
     stages_[stage].push_back(j);
+    stages_[stage].back().chain = cur_chain_;
+    if (cur_chain_ >= 0) chains_[size_t(cur_chain_)].jobs.emplace_back(int(stage), stages_[stage].size() - 1);
+}
+bool SszPlan::chain_field(int c, uint64_t* field_off, size_t* nbytes) const {
+    if (c < 0 || size_t(c) >= chains_.size() || chains_[size_t(c)].copy < 0) return false;
+    const HostCopy& hc = copies_[size_t(chains_[size_t(c)].copy)];
+    *field_off = hc.field_off; *nbytes = hc.nbytes;
+    return true;
 }
 
 uint32_t SszPlan::wide_nodes(PSrc src, bool raw, uint64_t n, int level, int depth_target, size_t s) {
@@ -105,7 +116,9 @@ uint32_t SszPlan::wide_records(uint32_t type, uint64_t field_off, uint64_t n, in
     PJob j;
     j.type = type; j.src.in_arena = false; j.src.off = field_off; j.dst = arena_alloc(n); j.n_in = n;
     if (type == JOB_VALIDATORS) {
+        j.chain = cur_chain_;
         validator_jobs_.push_back(j);
+        if (cur_chain_ >= 0) chains_[size_t(cur_chain_)].jobs.emplace_back(-1, validator_jobs_.size() - 1);
         for (auto& c : copies_) if (c.field_off == field_off) c.validators = true;
     } else add_job(0, j);
     PSrc s; s.in_arena = true; s.off = j.dst;
@@ -149,8 +162,11 @@ int32_t ensure_zero_nodes(Engine& e) {
     return B200_SUCCESS;
 }
 
-int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, bool fields_resident,
-                     const std::vector<uint32_t>& outputs, uint8_t* out) {
+int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, CopyMode copy,
+                     const std::vector<uint32_t>& outputs, uint8_t* out,
+                     const std::vector<std::vector<uint32_t>>* dirty, DevBuf* selbuf) {
+    const bool sparse = dirty != nullptr;
+    if (sparse && (dirty->size() != chains_.size() || !selbuf || copy == COPY_ALL)) return B200_ERR_BAD_ARG;
     if (small_words_.size() / 8 > kSmallCap) { e.last_error = "ssz plan: too many small leaves"; return B200_ERR_BAD_ARG; }
     int32_t rc = ensure_zero_nodes(e);
     if (rc) return rc;
@@ -201,14 +217,14 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     };
     B200_CUDA_TRY(cudaEventRecord(e.ev0, s));
     bool validators_launched = false;
-    if (!fields_resident) {
+    if (copy != COPY_NONE) {
         // H2D on the copy stream; the Validator list (85 % of the bytes) goes first, in up to 16 slices, and the compute
         // stream hashes slice k as soon as its copy has landed: kernels hide under the PCIe transfer.
         cudaStream_t cs = e.copy_stream;
         B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], s));
         B200_CUDA_TRY(cudaStreamWaitEvent(cs, e.ev_copy[16], 0));  // buffers may still be in use by the previous call
         for (auto& c : copies_) {
-            if (!c.validators || validator_jobs_.size() != 1) continue;
+            if (!c.validators || validator_jobs_.size() != 1 || copy != COPY_ALL) continue;
             const PJob& pj = validator_jobs_[0];
             const uint64_t n = pj.n_in;
             const uint64_t per = ((n + 15) / 16 + kStageThreads - 1) / kStageThreads * kStageThreads;  // whole CTAs per slice
@@ -230,6 +246,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         }
         for (auto& c : copies_) {
             if (c.validators && validators_launched) continue;
+            if (copy == COPY_SMALL_ONLY && c.chain >= 0) continue;
             B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off, c.src, c.nbytes, cudaMemcpyHostToDevice, cs));
             if (c.nbytes % 32)
                 B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, cs));
@@ -237,9 +254,46 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], cs));
         B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[16], 0));
     }
+    if (sparse) {
+        // dirty paths of the big lists: per chain, job k recomputes the outputs above the dirty inputs of job k
+        std::vector<uint32_t> sel;           // all selection lists back to back
+        struct Launch { const PJob* pj; size_t off; uint32_t n; };
+        std::vector<Launch> launches;
+        for (size_t c = 0; c < chains_.size(); c++) {
+            std::vector<uint32_t> cur = (*dirty)[c];
+            for (auto& ref : chains_[c].jobs) {
+                if (cur.empty()) break;
+                const PJob& pj = ref.first < 0 ? validator_jobs_[ref.second] : stages_[size_t(ref.first)][ref.second];
+                if (pj.type == JOB_REDUCE && pj.nlev) {
+                    size_t w = 0;
+                    for (size_t i = 0; i < cur.size(); i++) {
+                        const uint32_t o = cur[i] >> pj.nlev;
+                        if (w == 0 || cur[w - 1] != o) cur[w++] = o;
+                    }
+                    cur.resize(w);
+                } else if (pj.type != JOB_REDUCE && pj.type != JOB_VALIDATORS) {
+                    return B200_ERR_BAD_ARG;
+                }
+                launches.push_back(Launch{&pj, sel.size(), uint32_t(cur.size())});
+                sel.insert(sel.end(), cur.begin(), cur.end());
+            }
+        }
+        if (!sel.empty()) {
+            B200_CUDA_TRY(selbuf->reserve(sel.size() * 4));
+            B200_CUDA_TRY(cudaMemcpyAsync(selbuf->p, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, s));
+            const uint32_t* d_sel = static_cast<const uint32_t*>(selbuf->p);
+            for (auto& l : launches) { launch_sparse(materialize(*l.pj), d_arena, d_sel + l.off, l.n, s); e.launches++; }
+            B200_CUDA_TRY(cudaStreamSynchronize(s));  // `sel` is pageable host memory: keep it alive until copied
+        }
+    }
     if (!validators_launched)
-        for (auto& pj : validator_jobs_) { launch_validators(materialize(pj), s); e.launches++; }
-    for (auto& stage : stages_) {
+        for (auto& pj : validator_jobs_) {
+            if (sparse && pj.chain >= 0) continue;
+            launch_validators(materialize(pj), s); e.launches++;
+        }
+    for (auto& stage_all : stages_) {
+        std::vector<PJob> stage;
+        for (auto& pj : stage_all) if (!(sparse && pj.chain >= 0)) stage.push_back(pj);
         // split into launches of at most kMaxJobsPerStage jobs
         for (size_t b = 0; b < stage.size(); b += kMaxJobsPerStage) {
             StageDesc sd{};
@@ -428,11 +482,18 @@ int32_t build_beacon_state_plan(SszPlan& p, const uint8_t* s, size_t len, int pr
     auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
     uint32_t big[5];
     int d_reg = depth_for(P.validator_registry_limit);
+    // the five big lists are chains 0..4 (B200_FIELD_* in the C ABI): their jobs can re-hash dirty paths only
+    p.begin_chain();
     big[0] = p.mix_in_length(p.wide_records(JOB_VALIDATORS, p.stage_field(s + so.var[2], sz(2)), sz(2) / 121, d_reg), sz(2) / 121);
+    p.begin_chain();
     big[1] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[3], sz(3)), (sz(3) + 31) / 32, d_reg - 2), sz(3) / 8);
+    p.begin_chain();
     big[2] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[4], sz(4)), (sz(4) + 31) / 32, d_reg - 5), sz(4));
+    p.begin_chain();
     big[3] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[5], sz(5)), (sz(5) + 31) / 32, d_reg - 5), sz(5));
+    p.begin_chain();
     big[4] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[6], sz(6)), (sz(6) + 31) / 32, d_reg - 2), sz(6) / 8);
+    p.end_chain();
     outputs.assign(1, assemble_state(p, s, so, P, big));
     return B200_SUCCESS;
 }

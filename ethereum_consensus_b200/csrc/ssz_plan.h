@@ -26,6 +26,7 @@ struct PJob {
     uint64_t dst = 0;  // node index in the arena
     uint64_t n_in = 0;
     uint32_t level = 0, nlev = 0, raw = 0;
+    int chain = -1;  // index into SszPlan::chains_ for the jobs of a big list (dirty-path re-hash), else -1
 };
 
 struct HostCopy {
@@ -34,7 +35,17 @@ struct HostCopy {
     uint64_t field_off;
     size_t zero_tail;  // bytes to clear after the copy (keeps the last partial chunk zero-padded)
     bool validators = false;  // the big Validator list: copied in slices so hashing overlaps the PCIe transfer
+    int chain = -1;
 };
+
+// One big list of a device-resident state: its staged bytes and the sequence of jobs that reduces them to <= kHandoff
+// nodes.  `jobs[k]` = (stage, index in that stage), stage -1 = validator_jobs_.  Job k+1 reads exactly job k's output.
+struct PChain {
+    int copy = -1;
+    std::vector<std::pair<int, size_t>> jobs;
+};
+
+enum CopyMode { COPY_ALL = 0, COPY_NONE = 1, COPY_SMALL_ONLY = 2 };
 
 class SszPlan {
 public:
@@ -65,11 +76,22 @@ public:
     // n+1 48-byte records (n vector elements + 1 extra key) hashed by one job; returns the vector root
     uint32_t wide_pubkeys_with_extra(uint64_t field_off, uint64_t n, int depth_target, uint32_t* extra);
 
+    // jobs and staged bytes added between begin_chain() and end_chain() belong to one big list
+    int begin_chain() { chains_.emplace_back(); cur_chain_ = int(chains_.size()) - 1; return cur_chain_; }
+    void end_chain() { cur_chain_ = -1; }
+    size_t n_chains() const { return chains_.size(); }
+    // device byte offset (in the field buffer) and byte length of chain c's staged list; false if the list is empty
+    bool chain_field(int c, uint64_t* field_off, size_t* nbytes) const;
+
     // ---- execution ----
-    // Uploads fields (+plan) and runs; `fields_resident`: skip the field H2D copies (device-resident state).
+    // Uploads fields (+plan) and runs; `copy`: which staged fields to copy H2D first (COPY_NONE: device-resident state,
+    // COPY_SMALL_ONLY: everything except the chains' lists).
+    // `dirty` (optional, one sorted-unique vector per chain: indices of changed first-job inputs — Validator records, or
+    // 32-byte chunks of a packed list): the chains' jobs then only recompute the paths above those inputs.
     // `outputs`: arena nodes to read back (32 bytes each, SSZ byte order) into `out`.
-    int32_t run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, bool fields_resident,
-                const std::vector<uint32_t>& outputs, uint8_t* out);
+    int32_t run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, CopyMode copy,
+                const std::vector<uint32_t>& outputs, uint8_t* out,
+                const std::vector<std::vector<uint32_t>>* dirty = nullptr, DevBuf* selbuf = nullptr);
 
     size_t field_bytes() const { return field_next_; }
     uint64_t arena_nodes() const { return arena_next_; }
@@ -87,6 +109,8 @@ private:
     std::vector<uint32_t> small_words_; // word-form image of small leaves
     std::vector<uint32_t> small_idx_;   // arena idx of each small leaf
     std::vector<HostCopy> copies_;
+    std::vector<PChain> chains_;
+    int cur_chain_ = -1;
     uint64_t arena_next_ = 65 + 8192;  // [0,65) zero hashes, [65, 65+8192) small leaves uploaded with the plan
     size_t field_next_ = 0;
 

@@ -10,6 +10,8 @@ Every hash is computed on the GPU; there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+
+import numpy as np
 from typing import Sequence
 
 from . import _lib
@@ -109,6 +111,30 @@ class DeviceBeaconState:
     def hash_tree_root(self) -> bytes:
         out = _out32()
         _rc(_lib.lib().b200_state_root(self._h, out), "state_root")
+        return bytes(out)
+
+    # ---- incremental re-hash: patch the resident state, then re-hash only the dirty paths ----
+    FIELDS = {"validators": (0, 121), "balances": (1, 8), "previous_epoch_participation": (2, 1),
+              "current_epoch_participation": (3, 1), "inactivity_scores": (4, 8)}
+
+    def update_elements(self, field: str, indices, values) -> None:
+        """Overwrite elements `indices` of one of the five big lists; `values` = their SSZ encodings back to back
+        (121-byte Validator records, little-endian u64, or participation-flag bytes)."""
+        fid, elem = self.FIELDS[field]
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        vals = np.frombuffer(values, dtype=np.uint8) if isinstance(values, (bytes, bytearray)) else np.ascontiguousarray(values).view(np.uint8).reshape(-1)
+        if vals.size != idx.size * elem:
+            raise ValueError(f"{field}: expected {idx.size * elem} value bytes, got {vals.size}")
+        _rc(_lib.lib().b200_state_update_elements(self._h, fid, _lib.ptr(idx), _lib.ptr(vals), idx.size), "state_update_elements")
+
+    def update_bytes(self, ssz_offset: int, data) -> None:
+        """Overwrite bytes [ssz_offset, ssz_offset+len(data)) of the uploaded serialization (any field, same layout)."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        _rc(_lib.lib().b200_state_update_bytes(self._h, ssz_offset, _lib.ptr(buf), buf.size), "state_update_bytes")
+
+    def hash_tree_root_incremental(self) -> bytes:
+        out = _out32()
+        _rc(_lib.lib().b200_state_root_incremental(self._h, out), "state_root_incremental")
         return bytes(out)
 
     def close(self) -> None:

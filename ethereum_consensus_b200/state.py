@@ -157,6 +157,34 @@ def serialize(st: SynthState) -> np.ndarray:
     return out
 
 
+def layout(st: SynthState) -> Dict[str, tuple]:
+    """{field: (byte offset, byte length)} of every part of `serialize(st)` — the coordinates `b200_state_update_bytes`
+    takes (variable-size fields by name, fixed-size ones by the names used in `SynthState.fixed`)."""
+    names_var = ["historical_roots", "eth1_data_votes", "validators", "balances", "previous_epoch_participation",
+                 "current_epoch_participation", "inactivity_scores", "latest_execution_payload_header", "historical_summaries"]
+    var_len = [st.historical_roots.nbytes, st.eth1_data_votes.nbytes, st.validators.nbytes, st.balances.nbytes,
+               st.previous_epoch_participation.nbytes, st.current_epoch_participation.nbytes, st.inactivity_scores.nbytes,
+               len(st.payload_header_fixed) + len(st.extra_data), st.historical_summaries.nbytes]
+    f = st.fixed
+    OFF = None
+    parts = [("genesis_time", len(f["genesis_time"])), ("genesis_validators_root", 32), ("slot", 8), ("fork", len(f["fork"])),
+             ("latest_block_header", len(f["latest_block_header"])), ("block_roots", st.block_roots.nbytes),
+             ("state_roots", st.state_roots.nbytes), OFF, ("eth1_data", len(f["eth1_data"])), OFF, ("eth1_deposit_index", 8), OFF, OFF,
+             ("randao_mixes", st.randao_mixes.nbytes), ("slashings", st.slashings.nbytes), OFF, OFF, ("justification_bits", 1),
+             ("previous_justified_checkpoint", 40), ("current_justified_checkpoint", 40), ("finalized_checkpoint", 40), OFF,
+             ("current_sync_committee", len(st.current_sync_committee)), ("next_sync_committee", len(st.next_sync_committee)), OFF,
+             ("next_withdrawal_index", 8), ("next_withdrawal_validator_index", 8), OFF]
+    out, pos, k = {}, 0, 0
+    for p in parts:
+        if p is OFF:
+            out["offset:" + names_var[k]] = (pos, 4); k += 1; pos += 4
+        else:
+            out[p[0]] = (pos, p[1]); pos += p[1]
+    for name, ln in zip(names_var, var_len):
+        out[name] = (pos, ln); pos += ln
+    return out
+
+
 def to_oracle_value(st: SynthState) -> dict:
     """The same state as the dict-of-python-values the oracle's SSZ type system consumes (small N only)."""
     f = st.fixed

@@ -94,6 +94,23 @@ B200_API int32_t b200_state_upload_deneb(const uint8_t* ssz, size_t len, int32_t
 B200_API int32_t b200_state_root(b200_state* handle, uint8_t out[32]);
 B200_API void b200_state_free(b200_state* handle);
 
+/* Incremental re-hash of a device-resident state (SURVEY.md §8b `b200_state_update_leaves`, §8f-2): the two
+ * `state.hash_tree_root()` calls per block (deneb/spec/mod.rs:3215,3288) then cost O(changed x depth), not O(N).
+ *  - b200_state_update_elements: overwrite elements `indices[i]` of one of the five big lists with `values`
+ *    (n x 121 / 8 / 1 bytes, SSZ encoding of Validator / u64 / participation flags).  List lengths do not change.
+ *  - b200_state_update_bytes: overwrite bytes [ssz_offset, ssz_offset + n) of the serialization that was uploaded
+ *    (any field; must not change a variable-size field's offset or length — re-upload for that).
+ *  - b200_state_root_incremental: root after the updates.  Dirty paths of the big lists only; everything small
+ *    (~1 % of the hashes) is re-hashed in full.  b200_state_root stays the full O(N) re-hash. */
+#define B200_FIELD_VALIDATORS 0
+#define B200_FIELD_BALANCES 1
+#define B200_FIELD_PREVIOUS_EPOCH_PARTICIPATION 2
+#define B200_FIELD_CURRENT_EPOCH_PARTICIPATION 3
+#define B200_FIELD_INACTIVITY_SCORES 4
+B200_API int32_t b200_state_update_elements(b200_state* handle, int32_t field, const uint64_t* indices, const uint8_t* values, size_t n);
+B200_API int32_t b200_state_update_bytes(b200_state* handle, uint64_t ssz_offset, const uint8_t* data, size_t n);
+B200_API int32_t b200_state_root_incremental(b200_state* handle, uint8_t out[32]);
+
 /* Multi-GPU sharding of hash_tree_root(BeaconState): rank r of `world` hashes its contiguous
  * power-of-two-aligned slice of the five big lists and returns one subtree root per list
  * (out_roots: 5 x 32 bytes, order validators, balances, previous/current participation, inactivity_scores);

@@ -110,3 +110,93 @@ def test_sharded_state_small(engine, n, world):
     want = so.beacon_state_type("mainnet").htr(S.to_oracle_value(st))
     roots = b"".join(ssz.shard_roots(b, "mainnet", r, world) for r in range(world))
     assert ssz.combine_roots(b, "mainnet", world, roots) == want
+
+
+@pytest.mark.parametrize("n,preset,oracle_check", [(5, "minimal", True), (70, "minimal", True), (333, "mainnet", True),
+                                                   (5000, "mainnet", False), (70001, "mainnet", False)])
+def test_incremental_state_root(engine, n, preset, oracle_check):
+    """patch a device-resident state, re-hash only the dirty paths.  After every round the
+    incremental root must equal (a) a from-scratch GPU hash of the patched serialization and (b), for the small states,
+    the Python oracle's root of the identically patched value."""
+    from ethereum_consensus_b200._lib import EngineError
+    st = S.synth_state(n, preset, n_historical_summaries=3, n_historical_roots=2)
+    b = S.serialize(st).copy()
+    lay = S.layout(st)
+    dev = ssz.DeviceBeaconState(b, preset)
+    rng = np.random.default_rng(n)
+    typ = so.beacon_state_type(preset)
+    assert dev.hash_tree_root_incremental() == dev.hash_tree_root() == ssz.hash_tree_root_beacon_state(b, preset)
+
+    def check():
+        got = dev.hash_tree_root_incremental()
+        assert got == ssz.hash_tree_root_beacon_state(b, preset)
+        assert bytes(S.serialize(st)) == bytes(b)
+        if oracle_check:
+            assert got == typ.htr(S.to_oracle_value(st))
+        assert dev.hash_tree_root_incremental() == got      # nothing dirty: same root
+        assert dev.hash_tree_root() == got                  # and the full re-hash agrees
+
+    vbytes = st.validators.view(np.uint8).reshape(n, 121)
+    for rnd in range(3):
+        # validators: a few records change (effective balance, slashed flag, epochs, credentials)
+        k = min(n, 1 + 8 * rnd + (n > 1000) * 300)
+        idx = np.sort(rng.choice(n, k, replace=False)).astype(np.uint64)
+        if rnd == 0:
+            idx[-1] = n - 1                                    # the last record (ragged tail of the tree)
+        recs = vbytes[idx.astype(np.int64)].copy()
+        recs[:, 48:80] = rng.integers(0, 256, (len(idx), 32), dtype=np.uint8)
+        recs[:, 80:88] = np.frombuffer(rng.integers(0, 32 * 10**9, len(idx), dtype=np.uint64).astype("<u8").tobytes(), dtype=np.uint8).reshape(-1, 8)
+        recs[:, 88] ^= 1
+        dev.update_elements("validators", idx, recs)
+        vbytes[idx.astype(np.int64)] = recs
+        o = lay["validators"][0]
+        for i, r in zip(idx, recs):
+            b[o + 121 * int(i): o + 121 * int(i) + 121] = r
+        # packed lists: scattered elements, duplicates allowed (last write wins only if values agree: use unique)
+        for name, arr in (("balances", st.balances), ("inactivity_scores", st.inactivity_scores),
+                          ("previous_epoch_participation", st.previous_epoch_participation),
+                          ("current_epoch_participation", st.current_epoch_participation)):
+            m = min(n, 3 + 40 * rnd + (n > 1000) * 2000)
+            ii = np.unique(rng.choice(n, m)).astype(np.uint64)
+            if rnd == 1:
+                ii = np.unique(np.append(ii, [0, n - 1])).astype(np.uint64)
+            vals = rng.integers(0, 8 if arr.dtype == np.uint8 else 2**40, len(ii)).astype(arr.dtype)
+            dev.update_elements(name, ii, vals)
+            arr[ii.astype(np.int64)] = vals
+            o, ln = lay[name]
+            b[o:o + ln] = np.frombuffer(arr.tobytes(), dtype=np.uint8)
+        # small fields through the byte interface: slot, one block root, one randao mix
+        slot = int(rng.integers(1, 2**40)).to_bytes(8, "little")
+        dev.update_bytes(lay["slot"][0], slot)
+        st.fixed["slot"] = slot
+        b[lay["slot"][0]: lay["slot"][0] + 8] = np.frombuffer(slot, dtype=np.uint8)
+        for name, arr in (("block_roots", st.block_roots), ("randao_mixes", st.randao_mixes)):
+            j = int(rng.integers(0, arr.shape[0]))
+            v = rng.integers(0, 256, 32, dtype=np.uint8)
+            dev.update_bytes(lay[name][0] + 32 * j, v.tobytes())
+            arr[j] = v
+            b[lay[name][0] + 32 * j: lay[name][0] + 32 * j + 32] = v
+        if rnd == 2 and n >= 5:
+            # one byte range straddling two big lists: the last two validators and the first three balances
+            vo, vl = lay["validators"]
+            bo, _ = lay["balances"]
+            assert vo + vl == bo
+            lo, hi = bo - 2 * 121, bo + 3 * 8
+            patch = rng.integers(0, 256, hi - lo, dtype=np.uint8)
+            patch[88] &= 1; patch[121 + 88] &= 1             # `slashed` stays a boolean
+            dev.update_bytes(lo, patch.tobytes())
+            b[lo:hi] = patch
+            vbytes[n - 2:] = patch[:242].reshape(2, 121)
+            st.balances[:3] = np.frombuffer(patch[242:].tobytes(), dtype="<u8")
+        check()
+
+    # rejected updates leave the state untouched
+    root = dev.hash_tree_root_incremental()
+    with pytest.raises(EngineError):
+        dev.update_elements("balances", np.array([n], dtype=np.uint64), np.zeros(1, dtype="<u8"))
+    with pytest.raises(EngineError):
+        dev.update_bytes(lay["offset:balances"][0], (123).to_bytes(4, "little"))   # would move a variable-size field
+    with pytest.raises(EngineError):
+        dev.update_bytes(len(b) - 2, b"abcd")
+    assert dev.hash_tree_root_incremental() == root
+    dev.close()
