@@ -77,7 +77,13 @@ struct b200_state {
     StateOffsets so;
     std::vector<uint32_t> dirty[5];  // per big list: changed first-job inputs (records / 32-byte chunks), unsorted
     bool small_dirty = false;
-    ~b200_state() { free(shadow); }
+    std::vector<std::pair<const uint8_t*, const uint8_t*>> small_ranges;  // patched shadow bytes since the last root
+    bool pinned_head = false, pinned_tail = false;
+    ~b200_state() {
+        if (pinned_head) cudaHostUnregister(shadow);
+        if (pinned_tail) cudaHostUnregister(shadow + so.var[7]);
+        free(shadow);
+    }
 };
 
 namespace {
@@ -271,6 +277,10 @@ int32_t b200_state_upload_deneb(const uint8_t* ssz, size_t len, int32_t preset, 
     if (!h->shadow) { e.last_error = "out of host memory for the state shadow"; return B200_ERR_CUDA; }
     memcpy(h->shadow, ssz, h->so.var[2]);
     memcpy(h->shadow + h->so.var[7], ssz + h->so.var[7], len - h->so.var[7]);
+    // page-lock the two populated ranges (a few MB) so that re-staging a patched small field is a real async DMA
+    h->pinned_head = cudaHostRegister(h->shadow, h->so.var[2], cudaHostRegisterDefault) == cudaSuccess;
+    h->pinned_tail = cudaHostRegister(h->shadow + h->so.var[7], len - h->so.var[7], cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();  // registration is an optimisation: pageable copies work too
     rc = build_beacon_state_plan(h->plan, h->shadow, len, preset, h->outputs);  // same layout: it depends on lengths only
     if (rc) return rc;
     h->uploaded = true;
@@ -341,6 +351,7 @@ int32_t b200_state_update_bytes(b200_state* h, uint64_t ssz_offset, const uint8_
         if (x >= y) return;
         saved.insert(saved.end(), h->shadow + x, h->shadow + y);
         memcpy(h->shadow + x, data + (x - lo), y - x);
+        h->small_ranges.emplace_back(h->shadow + x, h->shadow + y);
     };
     auto restore_small = [&](uint64_t a, uint64_t b, size_t& pos) {
         const uint64_t x = std::max(a, lo), y = std::min(b, hi);
@@ -358,6 +369,7 @@ int32_t b200_state_update_bytes(b200_state* h, uint64_t ssz_offset, const uint8_
             size_t pos = 0;
             restore_small(0, h->so.var[2], pos);
             restore_small(h->so.var[7], h->len, pos);
+            // (the ranges stay recorded: re-copying unchanged bytes is harmless)
             e.last_error = "state_update_bytes: the update changes a variable-size field's offset or length; re-upload instead";
             return B200_ERR_BAD_ARG;
         }
@@ -405,10 +417,11 @@ int32_t b200_state_root_incremental(b200_state* h, uint8_t out[32]) {
         dirty[size_t(f)].erase(std::unique(dirty[size_t(f)].begin(), dirty[size_t(f)].end()), dirty[size_t(f)].end());
     }
     rc = h->plan.run(e, h->arena, h->fields, h->planbuf, h->small_dirty ? COPY_SMALL_ONLY : COPY_NONE, h->outputs, out,
-                     &dirty, &h->selbuf);
+                     &dirty, &h->selbuf, &h->small_ranges);
     if (rc) return rc;
     for (auto& d : h->dirty) d.clear();
     h->small_dirty = false;
+    h->small_ranges.clear();
     return B200_SUCCESS;
 }
 

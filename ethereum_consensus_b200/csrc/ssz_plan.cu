@@ -1,6 +1,8 @@
 // Host planner + executor for device-side SSZ hash_tree_root (see ssz_plan.h).
 #include "ssz_plan.h"
 
+#include <cstdlib>
+
 #include <algorithm>
 
 namespace b200 {
@@ -164,7 +166,8 @@ int32_t ensure_zero_nodes(Engine& e) {
 
 int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, CopyMode copy,
                      const std::vector<uint32_t>& outputs, uint8_t* out,
-                     const std::vector<std::vector<uint32_t>>* dirty, DevBuf* selbuf) {
+                     const std::vector<std::vector<uint32_t>>* dirty, DevBuf* selbuf,
+                     const std::vector<std::pair<const uint8_t*, const uint8_t*>>* changed_host_ranges) {
     const bool sparse = dirty != nullptr;
     if (sparse && (dirty->size() != chains_.size() || !selbuf || copy == COPY_ALL)) return B200_ERR_BAD_ARG;
     if (small_words_.size() / 8 > kSmallCap) { e.last_error = "ssz plan: too many small leaves"; return B200_ERR_BAD_ARG; }
@@ -185,14 +188,42 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     for (size_t i = 0; i < order.size(); i++) wave_end[size_t(op_wave_[order[i]])] = uint32_t(i + 1);
     for (int w = 1; w < nwaves; w++) wave_end[size_t(w)] = std::max(wave_end[size_t(w)], wave_end[size_t(w - 1)]);
 
-    // pinned staging image: [small words | ops | wave_end | out(32 B x outputs)]
+    // dirty-path selection lists (host only): per chain, the outputs of job k that lie above the dirty inputs of job k
+    std::vector<uint32_t> sel;           // all selection lists back to back
+    struct Launch { const PJob* pj; size_t off; uint32_t n; };
+    std::vector<Launch> launches;
+    if (sparse) {
+        for (size_t c = 0; c < chains_.size(); c++) {
+            std::vector<uint32_t> cur = (*dirty)[c];
+            for (auto& ref : chains_[c].jobs) {
+                if (cur.empty()) break;
+                const PJob& pj = ref.first < 0 ? validator_jobs_[ref.second] : stages_[size_t(ref.first)][ref.second];
+                if (pj.type == JOB_REDUCE && pj.nlev) {
+                    size_t w = 0;
+                    for (size_t i = 0; i < cur.size(); i++) {
+                        const uint32_t o = cur[i] >> pj.nlev;
+                        if (w == 0 || cur[w - 1] != o) cur[w++] = o;
+                    }
+                    cur.resize(w);
+                } else if (pj.type != JOB_REDUCE && pj.type != JOB_VALIDATORS) {
+                    return B200_ERR_BAD_ARG;
+                }
+                launches.push_back(Launch{&pj, sel.size(), uint32_t(cur.size())});
+                sel.insert(sel.end(), cur.begin(), cur.end());
+            }
+        }
+        if (!sel.empty()) B200_CUDA_TRY(selbuf->reserve(sel.size() * 4));
+    }
+
+    // pinned staging image: [small words | ops | wave_end | out(32 B x outputs) | selection lists]
     size_t sz_small = small_words_.size() * 4;
     size_t sz_ops = ops_.size() * sizeof(FinOp);
     size_t sz_wend = wave_end.size() * 4;
     size_t off_ops = (sz_small + 15) & ~size_t(15);
     size_t off_wend = off_ops + ((sz_ops + 15) & ~size_t(15));
     size_t off_out = off_wend + ((sz_wend + 15) & ~size_t(15));
-    size_t total = off_out + 32 * outputs.size();
+    size_t off_sel = (off_out + 32 * outputs.size() + 15) & ~size_t(15);
+    size_t total = off_sel + sel.size() * 4;
     B200_CUDA_TRY(e.staging.reserve(total));
     B200_CUDA_TRY(planbuf.reserve(off_out + 64));
     uint8_t* st = static_cast<uint8_t*>(e.staging.p);
@@ -200,6 +231,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     FinOp* hops = reinterpret_cast<FinOp*>(st + off_ops);
     for (size_t i = 0; i < order.size(); i++) hops[i] = ops_[order[i]];
     if (sz_wend) memcpy(st + off_wend, wave_end.data(), sz_wend);
+    if (!sel.empty()) memcpy(st + off_sel, sel.data(), sel.size() * 4);
 
     cudaStream_t s = e.stream;
     uint8_t* d_plan = static_cast<uint8_t*>(planbuf.p);
@@ -216,6 +248,9 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         return j;
     };
     B200_CUDA_TRY(cudaEventRecord(e.ev0, s));
+    static const bool trace = getenv("B200_SSZ_TRACE") && atoi(getenv("B200_SSZ_TRACE"));
+    static cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace && !tev[0]) for (auto& ev : tev) cudaEventCreate(&ev);
     bool validators_launched = false;
     if (copy != COPY_NONE) {
         // H2D on the copy stream; the Validator list (85 % of the bytes) goes first, in up to 16 slices, and the compute
@@ -247,6 +282,11 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         for (auto& c : copies_) {
             if (c.validators && validators_launched) continue;
             if (copy == COPY_SMALL_ONLY && c.chain >= 0) continue;
+            if (copy == COPY_SMALL_ONLY && changed_host_ranges) {
+                bool hit = false;
+                for (auto& r : *changed_host_ranges) hit = hit || (r.first < c.src + c.nbytes && c.src < r.second);
+                if (!hit) continue;
+            }
             B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off, c.src, c.nbytes, cudaMemcpyHostToDevice, cs));
             if (c.nbytes % 32)
                 B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, cs));
@@ -254,38 +294,14 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], cs));
         B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[16], 0));
     }
-    if (sparse) {
+    if (trace) cudaEventRecord(tev[0], s);
+    if (sparse && !sel.empty()) {
         // dirty paths of the big lists: per chain, job k recomputes the outputs above the dirty inputs of job k
-        std::vector<uint32_t> sel;           // all selection lists back to back
-        struct Launch { const PJob* pj; size_t off; uint32_t n; };
-        std::vector<Launch> launches;
-        for (size_t c = 0; c < chains_.size(); c++) {
-            std::vector<uint32_t> cur = (*dirty)[c];
-            for (auto& ref : chains_[c].jobs) {
-                if (cur.empty()) break;
-                const PJob& pj = ref.first < 0 ? validator_jobs_[ref.second] : stages_[size_t(ref.first)][ref.second];
-                if (pj.type == JOB_REDUCE && pj.nlev) {
-                    size_t w = 0;
-                    for (size_t i = 0; i < cur.size(); i++) {
-                        const uint32_t o = cur[i] >> pj.nlev;
-                        if (w == 0 || cur[w - 1] != o) cur[w++] = o;
-                    }
-                    cur.resize(w);
-                } else if (pj.type != JOB_REDUCE && pj.type != JOB_VALIDATORS) {
-                    return B200_ERR_BAD_ARG;
-                }
-                launches.push_back(Launch{&pj, sel.size(), uint32_t(cur.size())});
-                sel.insert(sel.end(), cur.begin(), cur.end());
-            }
-        }
-        if (!sel.empty()) {
-            B200_CUDA_TRY(selbuf->reserve(sel.size() * 4));
-            B200_CUDA_TRY(cudaMemcpyAsync(selbuf->p, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, s));
-            const uint32_t* d_sel = static_cast<const uint32_t*>(selbuf->p);
-            for (auto& l : launches) { launch_sparse(materialize(*l.pj), d_arena, d_sel + l.off, l.n, s); e.launches++; }
-            B200_CUDA_TRY(cudaStreamSynchronize(s));  // `sel` is pageable host memory: keep it alive until copied
-        }
+        B200_CUDA_TRY(cudaMemcpyAsync(selbuf->p, st + off_sel, sel.size() * 4, cudaMemcpyHostToDevice, s));
+        const uint32_t* d_sel = static_cast<const uint32_t*>(selbuf->p);
+        for (auto& l : launches) { launch_sparse(materialize(*l.pj), d_arena, d_sel + l.off, l.n, s); e.launches++; }
     }
+    if (trace) cudaEventRecord(tev[1], s);
     if (!validators_launched)
         for (auto& pj : validator_jobs_) {
             if (sparse && pj.chain >= 0) continue;
@@ -312,6 +328,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
             e.launches++;
         }
     }
+    if (trace) cudaEventRecord(tev[2], s);
     if (nwaves) {
         launch_finisher(d_arena, reinterpret_cast<const FinOp*>(d_plan + off_ops),
                         reinterpret_cast<const uint32_t*>(d_plan + off_wend), nwaves, s);
@@ -324,6 +341,13 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
                                       cudaMemcpyDeviceToHost, s));
     B200_CUDA_TRY(cudaStreamSynchronize(s));
     B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, e.ev0, e.ev1));
+    if (trace) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, e.ev0, tev[0]); cudaEventElapsedTime(&b, tev[0], tev[1]);
+        cudaEventElapsedTime(&c, tev[1], tev[2]); cudaEventElapsedTime(&d, tev[2], e.ev1);
+        fprintf(stderr, "[b200 ssz] uploads %.3f | dirty paths %.3f | dense stages %.3f | finisher %.3f | total %.3f ms (%s)\n",
+                a, b, c, d, e.last_kernel_ms, sparse ? "incremental" : "full");
+    }
     for (size_t i = 0; i < outputs.size(); i++) {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(st + off_out + 32 * i);
         for (int k = 0; k < 8; k++) {

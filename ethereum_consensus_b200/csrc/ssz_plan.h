@@ -88,10 +88,12 @@ public:
     // COPY_SMALL_ONLY: everything except the chains' lists).
     // `dirty` (optional, one sorted-unique vector per chain: indices of changed first-job inputs — Validator records, or
     // 32-byte chunks of a packed list): the chains' jobs then only recompute the paths above those inputs.
+    // `changed_host_ranges` (COPY_SMALL_ONLY): copy only the staged fields whose host bytes intersect one of these ranges.
     // `outputs`: arena nodes to read back (32 bytes each, SSZ byte order) into `out`.
     int32_t run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, CopyMode copy,
                 const std::vector<uint32_t>& outputs, uint8_t* out,
-                const std::vector<std::vector<uint32_t>>* dirty = nullptr, DevBuf* selbuf = nullptr);
+                const std::vector<std::vector<uint32_t>>* dirty = nullptr, DevBuf* selbuf = nullptr,
+                const std::vector<std::pair<const uint8_t*, const uint8_t*>>* changed_host_ranges = nullptr);
 
     size_t field_bytes() const { return field_next_; }
     uint64_t arena_nodes() const { return arena_next_; }
