@@ -355,11 +355,12 @@ def main():
             "value": value, "ms_per_step": ms_dev, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "tuples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * T},
             "clocks": clk.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_g1_validate", "achieved": alg_bytes / (dom / 1e3) / 1e9, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "k_g1_validate_r168", "achieved": alg_bytes / (dom / 1e3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": alg_bytes / (dom / 1e3) / 1e9 / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at T=4096,K=512 from one `ncu --set full`
-                         # capture (profiles/r1_k_g1_validate_main_T4096_ncu.txt): 110.2 MB + 166.4 MB
-                         "traffic": 276.6e6 if (T == 4096 and K == 512) else None,
+                         # capture (profiles/r1m_k_g1_validate_r168_ncu.txt): 112.5 MB read + 200.8 MB written (the kernel's
+                         # own output is 100 B of affine point + 4 B of code per key = 218 MB; the inputs are 100.7 MB)
+                         "traffic": 313.3e6 if (T == 4096 and K == 512) else None,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "note": "algorithmic bytes = T*(48K+128); this path is integer-pipe bound, see int_roofline",
                          "kernel_ms": dom, "share_of_step": dom / ms_dev},
