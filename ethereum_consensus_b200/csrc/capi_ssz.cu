@@ -79,10 +79,11 @@ struct b200_state {
     bool small_dirty = false;
     std::vector<std::pair<const uint8_t*, const uint8_t*>> small_ranges;  // patched shadow bytes since the last root
     bool pinned_head = false, pinned_tail = false;
-    ~b200_state() {
+    ~b200_state() {  // callers hold the engine lock and have selected the device
         if (pinned_head) cudaHostUnregister(shadow);
         if (pinned_tail) cudaHostUnregister(shadow + so.var[7]);
         free(shadow);
+        arena.release(); fields.release(); planbuf.release(); selbuf.release(); scatter.release();
     }
 };
 
@@ -268,7 +269,7 @@ int32_t b200_state_upload_deneb(const uint8_t* ssz, size_t len, int32_t preset, 
         if (rc) { e.last_error = "malformed deneb BeaconState SSZ"; return rc; }
         uint8_t root[32];
         rc = first.run(e, h->arena, h->fields, h->planbuf, COPY_ALL, outs, root);  // uploads + first hash
-        if (rc) { h->arena.release(); h->fields.release(); h->planbuf.release(); return rc; }
+        if (rc) return rc;  // ~b200_state releases the device buffers
     }
     // keep what is needed to re-plan without the caller's buffer: the serialization minus the big lists
     if (!parse_beacon_state(ssz, len, preset, h->so)) return B200_ERR_SSZ_MALFORMED;
@@ -302,7 +303,6 @@ void b200_state_free(b200_state* h) {
     Engine& e = engine();
     Guard g(e);
     if (e.ready) { cudaSetDevice(e.device); cudaStreamSynchronize(e.stream); }
-    h->arena.release(); h->fields.release(); h->planbuf.release(); h->selbuf.release(); h->scatter.release();
     delete h;
 }
 

@@ -119,3 +119,27 @@ def test_signing_root_shapes():
     assert len(d) == 32 and d[:4] == bytes.fromhex("01000000")
     r = so.compute_signing_root(bytes(32), d)
     assert r == so.hash_pair(bytes(32), d)
+
+
+@pytest.mark.parametrize("n,preset", [(0, "minimal"), (5, "minimal"), (70, "mainnet"), (1000, "mainnet")])
+def test_state_layout_matches_serialization(n, preset):
+    """`state.layout` gives the byte coordinates `b200_state_update_bytes` takes: every part must sit where
+    `serialize` put it, the offset words must point at the variable-size fields, and the parts must tile the buffer."""
+    import numpy as np
+    from ethereum_consensus_b200 import state as S
+    st = S.synth_state(n, preset, n_historical_summaries=3, n_historical_roots=2)
+    b = S.serialize(st)
+    lay = S.layout(st)
+    spans = sorted(lay.values())
+    assert spans[0][0] == 0 and all(a[0] + a[1] == c[0] for a, c in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] == len(b)
+    for name in ("balances", "inactivity_scores", "previous_epoch_participation", "current_epoch_participation", "validators",
+                 "block_roots", "randao_mixes", "slashings", "historical_summaries"):
+        o, ln = lay[name]
+        assert bytes(b[o:o + ln]) == getattr(st, name).tobytes()
+        if "offset:" + name in lay:
+            oo, _ = lay["offset:" + name]
+            assert int.from_bytes(bytes(b[oo:oo + 4]), "little") == o
+    for name in ("slot", "fork", "latest_block_header", "eth1_data", "finalized_checkpoint", "next_withdrawal_index"):
+        o, ln = lay[name]
+        assert bytes(b[o:o + ln]) == st.fixed[name]
+    assert lay["validators"][1] == 121 * n and lay["balances"][1] == 8 * n
