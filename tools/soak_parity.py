@@ -162,6 +162,36 @@ for t in range(n):
     hist[b] = hist.get(b, 0) + 1
     bad += a != b
 report("fast_aggregate_verify (K<=8)", n, bad, hist); total_bad += bad
+# ---- 5. triangulation: the spec-level Python big-int oracle (in_subgroup = [r]P by definition, generic square roots)
+#         against the C oracle on a sample of the same case generators
+from oracle import bls_oracle as bo  # noqa: E402
+n = int(500 * scale)
+keys, _, _ = valid_keys(n, seed=3)
+sample = [keys[i].tobytes() for i in range(n // 4)]
+rnd = rng.integers(0, 256, (n // 2, 48), dtype=np.uint8)
+rnd[:, 0] = ((rnd[:, 0] & 0x3f) | 0x80) & 0xbf
+sample += [r.tobytes() for r in rnd] + [mutate(keys[i].tobytes(), 48, i % 9) for i in range(n // 4)]
+bad = sum(bo.key_validate(c)[0] != O.orc_key_validate(c) for c in sample)
+report("py vs C: key_validate", len(sample), bad, {}); total_bad += bad
+sg = valid_sigs(n // 8)
+sample = [sg[i].tobytes() for i in range(n // 8)]
+rnd = rng.integers(0, 256, (n // 4, 96), dtype=np.uint8)
+rnd[:, 0] = ((rnd[:, 0] & 0x3f) | 0x80) & 0xbf
+rnd[:, 48] &= 0x1f
+sample += [r.tobytes() for r in rnd] + [mutate(sg[i % (n // 8)].tobytes(), 96, i % 9) for i in range(n // 8)]
+bad = 0
+for c in sample:
+    code, out = bo.aggregate([c])
+    b = O.orc_aggregate(c, 1, agg)
+    bad += code != b or (code == 0 and out != agg.raw)
+report("py vs C: sig decode + subgroup", len(sample), bad, {}); total_bad += bad
+bad = 0
+for i in range(n // 5):
+    m = rng.integers(0, 256, int(rng.integers(0, 120)), dtype=np.uint8).tobytes()
+    O.orc_hash_to_g2(m, len(m), o2)
+    (x, y) = bo.hash_to_g2(m)
+    bad += o2.raw != b"".join(v.to_bytes(48, "big") for v in (x[0], x[1], y[0], y[1]))
+report("py vs C: hash_to_G2", n // 5, bad, {}); total_bad += bad
 print(f"total mismatches {total_bad}   wall {time.time() - t_start:.0f} s   (blst codes: 0 ok, 1 bad encoding, 2 not on curve, 3 not in group, "
       f"5 verify fail, 6 pk is infinity)")
 sys.exit(1 if total_bad else 0)
