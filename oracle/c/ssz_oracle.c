@@ -261,9 +261,10 @@ static void validator_root(const uint8_t *v, uint8_t out[32]) {
     memcpy(leaf[6], v + 105, 8);
     memcpy(leaf[7], v + 113, 8);
     uint8_t l1[4][32], l2[2][32];
-    for (int i = 0; i < 4; i++) hash64(leaf[2 * i], l1[i]);
-    for (int i = 0; i < 2; i++) hash64(l1[2 * i], l2[i]);
-    hash64(l2[0], out);
+    /* adjacent 32-byte rows are one contiguous 64-byte block */
+    for (int i = 0; i < 4; i++) hash64((const uint8_t *)leaf + 64 * i, l1[i]);
+    for (int i = 0; i < 2; i++) hash64((const uint8_t *)l1 + 64 * i, l2[i]);
+    hash64((const uint8_t *)l2, out);
 }
 typedef struct { const uint8_t *in; uint8_t *out; size_t stride; int kind; } elem_ctx;
 static void elem_range(void *c, size_t lo, size_t hi) {
@@ -279,7 +280,7 @@ static void elem_range(void *c, size_t lo, size_t hi) {
             uint8_t l[4][32], m[2][32];
             memset(l, 0, sizeof l);
             memcpy(l[0], p, 32); memcpy(l[1], p + 32, 8); memcpy(l[2], p + 40, 32);
-            hash64(l[0], m[0]); hash64(l[2], m[1]);
+            hash64((const uint8_t *)l, m[0]); hash64((const uint8_t *)l + 64, m[1]);
             orc_hash_pair(m[0], m[1], x->out + 32 * i);
         } break;
         }
