@@ -3,14 +3,14 @@ ethereum_consensus_b200/csrc/*.cuh — the same source the kernels compile) agai
 tens of thousands of random and adversarial inputs.  SURVEY.md §8c asks for >= 10^4 such cases because the reference's
 own offline KATs only pin the accept side.
 
-    python tools/soak_parity.py [scale] > profiles/r1_soak_parity.txt        (scale 1.0 ~ a few minutes on 8 cores)
+    python tests/soak_parity.py [scale] > profiles/r1_soak_parity.txt        (scale 1.0 ~ a few minutes on 8 cores)
 """
 import ctypes as C, hashlib, subprocess, sys, time
 from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent  # tests/ -> repo root
 sys.path.insert(0, str(ROOT))
 P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
 R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
