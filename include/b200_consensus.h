@@ -97,7 +97,8 @@ B200_API void b200_state_free(b200_state* handle);
 /* Incremental re-hash of a device-resident state (SURVEY.md §8b `b200_state_update_leaves`, §8f-2): the two
  * `state.hash_tree_root()` calls per block (deneb/spec/mod.rs:3215,3288) then cost O(changed x depth), not O(N).
  *  - b200_state_update_elements: overwrite elements `indices[i]` of one of the five big lists with `values`
- *    (n x 121 / 8 / 1 bytes, SSZ encoding of Validator / u64 / participation flags).  List lengths do not change.
+ *    (n x 121 / 8 / 1 bytes, SSZ encoding of Validator / u64 / participation flags).  List lengths do not change;
+ *    an index may appear more than once only with identical values (elements are written in parallel).
  *  - b200_state_update_bytes: overwrite bytes [ssz_offset, ssz_offset + n) of the serialization that was uploaded
  *    (any field; must not change a variable-size field's offset or length — re-upload for that).
  *  - b200_state_root_incremental: root after the updates.  Dirty paths of the big lists only; everything small
