@@ -23,9 +23,13 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> Path:
-    """`defines`/`suffix`: alternate tuning build, e.g. build(defines=["B200_FP_SQR_VIA_MUL"], suffix="_sqrmul")."""
+def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "", ptxas_opt=None) -> Path:
+    """`defines`/`suffix`: alternate tuning build, e.g. build(defines=["B200_FP_SQR_VIA_MUL"], suffix="_sqrmul").
+    `ptxas_opt`: {"bls_g1.cu": 1, ...} compiles those translation units with `-Xptxas -O<n>` (A/B knob: at -O1 ptxas
+    stops interleaving more carry chains than it has predicate registers — 34 k instead of 51 k instructions in the
+    per-key kernel, same IMAD.WIDE count).  Use a `suffix` so the default objects are not reused."""
     global LIB, OBJ
+    ptxas_opt = dict(ptxas_opt or {})
     if suffix:
         LIB = PKG / f"libb200_consensus{suffix}.so"
         OBJ = PKG / f"build{suffix}"
@@ -41,6 +45,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = 
     def cc(job):
         s, o = job
         cmd = [NVCC, *FLAGS, *[f"-D{d}" for d in defines], "-c", str(s), "-o", str(o)]
+        if s.name in ptxas_opt:
+            cmd[1:1] = ["-Xptxas", f"-O{int(ptxas_opt[s.name])}"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -65,4 +71,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = 
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     suf = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")), "")
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, suffix=suf))
+    # --ptxas-opt=bls_g1.cu:1,bls_g2.cu:1
+    popt = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--ptxas-opt=")), "")
+    popt = {kv.split(":")[0]: int(kv.split(":")[1]) for kv in popt.split(",") if kv}
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, suffix=suf, ptxas_opt=popt))
