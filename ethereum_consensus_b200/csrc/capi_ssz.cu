@@ -289,13 +289,36 @@ int32_t b200_state_upload_deneb(const uint8_t* ssz, size_t len, int32_t preset, 
     return B200_SUCCESS;
 }
 
+// pending small-field updates: re-plan from the shadow (same arena / field layout, fresh small leaves)
+static int32_t replan_if_small_dirty(Engine& e, b200_state* h) {
+    if (!h->small_dirty) return B200_SUCCESS;
+    SszPlan np;
+    std::vector<uint32_t> outs;
+    int32_t rc = build_beacon_state_plan(np, h->shadow, h->len, h->preset, outs);
+    if (rc) return rc;
+    if (np.arena_nodes() != h->plan.arena_nodes() || np.field_bytes() != h->plan.field_bytes() || outs != h->outputs) {
+        e.last_error = "state root: plan layout changed";
+        return B200_ERR_BAD_ARG;
+    }
+    h->plan = std::move(np);
+    return B200_SUCCESS;
+}
+
 int32_t b200_state_root(b200_state* h, uint8_t out[32]) {
     Engine& e = engine();
     Guard g(e);
     int32_t rc = check_ready(e);
     if (rc) return rc;
     if (!h || !h->uploaded || !out) return B200_ERR_BAD_ARG;
-    return h->plan.run(e, h->arena, h->fields, h->planbuf, COPY_NONE, h->outputs, out);
+    rc = replan_if_small_dirty(e, h);  // updates made through b200_state_update_* are honoured here too
+    if (rc) return rc;
+    rc = h->plan.run(e, h->arena, h->fields, h->planbuf, h->small_dirty ? COPY_SMALL_ONLY : COPY_NONE, h->outputs, out,
+                     nullptr, nullptr, &h->small_ranges);
+    if (rc) return rc;
+    for (auto& d : h->dirty) d.clear();  // a full re-hash covers every dirty path
+    h->small_dirty = false;
+    h->small_ranges.clear();
+    return B200_SUCCESS;
 }
 
 void b200_state_free(b200_state* h) {
@@ -399,17 +422,8 @@ int32_t b200_state_root_incremental(b200_state* h, uint8_t out[32]) {
     int32_t rc = check_ready(e);
     if (rc) return rc;
     if (!h || !h->uploaded || !out) return B200_ERR_BAD_ARG;
-    if (h->small_dirty) {  // re-plan from the shadow: same arena / field layout, fresh small leaves
-        SszPlan np;
-        std::vector<uint32_t> outs;
-        rc = build_beacon_state_plan(np, h->shadow, h->len, h->preset, outs);
-        if (rc) return rc;
-        if (np.arena_nodes() != h->plan.arena_nodes() || np.field_bytes() != h->plan.field_bytes() || outs != h->outputs) {
-            e.last_error = "state_root_incremental: plan layout changed";
-            return B200_ERR_BAD_ARG;
-        }
-        h->plan = std::move(np);
-    }
+    rc = replan_if_small_dirty(e, h);
+    if (rc) return rc;
     std::vector<std::vector<uint32_t>> dirty(h->plan.n_chains());
     for (int f = 0; f < 5 && size_t(f) < dirty.size(); f++) {
         dirty[size_t(f)] = h->dirty[f];
