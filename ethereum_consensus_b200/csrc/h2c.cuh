@@ -146,12 +146,128 @@ B200_BIG void iso3_map(G2Jac& out, const Fp2& x, const Fp2& y) {
     if (fp2_is_zero(out.z)) jac_set_inf(out);
 }
 
+#if defined(B200_SSWU_FRACTION)
+// ---- A/B variant (default off; round-2 experiment): simplified SWU with x kept as a fraction, so the Fp2 inversion
+// (one of the three exponentiations of the map) disappears.  RFC 9380 F.2 straight-line shape:
+//   x1 = N/D, N = B (tv1 + 1), D = -A tv1 (D = Z A when tv1 = 0);  g(x1) = U/V, U = N^3 + A N D^2 + B D^3, V = D^3.
+// Square root of W = U/V without inverting V: with V~ = conj(V), nV = norm(V):  W = W'/nV^2 for W' = U V~ nV, so
+// sqrt(W) = sqrt(W')/nV.  Complex method on W' (norm root s' = s_n nV with s_n^2 = +-norm(U V~)), d = (W'_0 + s')/2,
+// and ONE exponentiation of q = d nV^2:  r = q^((p-3)/4) = t chi(nV)/nV  with t = d^((p-3)/4).  Up to the irrelevant
+// global sign chi(nV) the affine root is (d r, W'_1 r/2) if (d r nV)^2 = d, else (-W'_1 r/2, d r)  [cf. fp2.cuh].
+// Output: x as the fraction xn/xd, y affine (so sgn0 can fix its sign).
+B200_BIG void sswu_map_frac(Fp2& xn, Fp2& xd, Fp2& y, const Fp2& t) {
+    const Fp2 Zc = B200_FP2_SSWU_Z, A = B200_FP2_SSWU_A, B = B200_FP2_SSWU_B;
+    Fp2 t2, zt2, tv1, N, D, one = fp2_one();
+    fp2_sqr(t2, t);
+    fp2_mul(zt2, Zc, t2);
+    fp2_sqr(tv1, zt2);
+    fp2_add(tv1, tv1, zt2);
+    fp2_add(N, tv1, one);
+    fp2_mul(N, N, B);
+    if (fp2_is_zero(tv1)) fp2_mul(D, Zc, A); else { fp2_mul(D, A, tv1); fp2_neg(D, D); }
+    Fp2 N2, D2, D3, U, u1;
+    fp2_sqr(N2, N); fp2_sqr(D2, D); fp2_mul(D3, D2, D);
+    fp2_mul(U, N2, N);                 // N^3
+    fp2_mul(u1, A, N); fp2_mul(u1, u1, D2);
+    fp2_add(U, U, u1);
+    fp2_mul(u1, B, D3);
+    fp2_add(U, U, u1);                 // U;  V = D3
+    Fp nV, tt;
+    fp_sqr(nV, D3.c0); fp_sqr(tt, D3.c1); fp_add(nV, nV, tt);
+    Fp2 Vc = D3, Wn, W;
+    fp_neg(Vc.c1, Vc.c1);
+    fp2_mul(Wn, U, Vc);                // U conj(V)
+    Fp n, s, c;
+    fp_sqr(n, Wn.c0); fp_sqr(tt, Wn.c1); fp_add(n, n, tt);
+    fp_pow(s, n, B200_EXP_TABLE(exp_sqrt));
+    fp_sqr(c, s);
+    const bool is_sq = fp_eq(c, n);
+    if (!is_sq) {
+        const Fp2 z3 = B200_FP2_SSWU_Z3;
+        const Fp cs = B200_FP_SSWU_SQRT_NEG_NORM_Z3;
+        fp2_mul(Wn, z3, Wn);
+        fp_mul(s, s, cs);
+    }
+    fp_mul(W.c0, Wn.c0, nV); fp_mul(W.c1, Wn.c1, nV);   // W' = (Z^3) U conj(V) nV
+    fp_mul(s, s, nV);                                   // s' = sqrt(norm(W'))
+    Fp2 yy;
+    bool ok = false;
+    if (!fp_is_zero(W.c1)) {
+        Fp d, q, r, u, chk, h, dr;
+        fp_add(d, W.c0, s); fp_half(d, d);
+        fp_sqr(q, nV); fp_mul(q, q, d);
+        fp_pow(r, q, B200_EXP_TABLE(exp_p_minus_3_div_4));
+        fp_mul(dr, d, r);
+        fp_mul(u, dr, nV);
+        fp_sqr(chk, u);
+        fp_mul(h, W.c1, r); fp_half(h, h);
+        if (fp_eq(chk, d)) { yy.c0 = dr; yy.c1 = h; } else { fp_neg(yy.c0, h); yy.c1 = dr; }
+        // verify in fraction form: yy^2 nV^2 == W'  (yy = sqrt(W')/nV)
+        Fp2 sq; Fp nV2;
+        fp2_sqr(sq, yy); fp_sqr(nV2, nV);
+        fp_mul(sq.c0, sq.c0, nV2); fp_mul(sq.c1, sq.c1, nV2);
+        ok = fp2_eq(sq, W);
+    }
+    if (!ok) {   // real W' (probability ~2^-381) or an inconsistency: the general affine routine
+        Fp2 xa, ya;
+        sswu_map(xa, ya, t);
+        xn = xa; xd = fp2_one(); y = ya;
+        return;
+    }
+    if (is_sq) {
+        xn = N;
+    } else {
+        Fp2 t3;
+        fp2_mul(xn, zt2, N);
+        fp2_mul(t3, t2, t);
+        fp2_mul(yy, yy, t3);
+    }
+    xd = D;
+    if (fp2_sgn0(t) != fp2_sgn0(yy)) fp2_neg(yy, yy);
+    y = yy;
+}
+// 3-isogeny with x = xn/xd: homogeneous Horner forms, Jacobian output Z = xd XD YD
+//   x' = XN / (xd XD),  y' = y YN / YD   with XN, YN, YD cubic forms and XD a quadratic form in (xn, xd)
+B200_BIG void iso3_map_frac(G2Jac& out, const Fp2& xn, const Fp2& xd, const Fp2& y) {
+    Fp2 z2, z3, t, XN, XD, YN, YD;
+    fp2_sqr(z2, xd); fp2_mul(z3, z2, xd);
+    auto cubic = [&](Fp2& r, const Fp2& k0, const Fp2& k1, const Fp2& k2, const Fp2& k3) {
+        Fp2 a;                                  // ((k3 xn + k2 xd) xn + k1 xd^2) xn + k0 xd^3
+        fp2_mul(r, k3, xn); fp2_mul(a, k2, xd); fp2_add(r, r, a);
+        fp2_mul(r, r, xn); fp2_mul(a, k1, z2); fp2_add(r, r, a);
+        fp2_mul(r, r, xn); fp2_mul(a, k0, z3); fp2_add(r, r, a);
+    };
+    { const Fp2 k0 = B200_FP2_ISO_XNUM0, k1 = B200_FP2_ISO_XNUM1, k2 = B200_FP2_ISO_XNUM2, k3 = B200_FP2_ISO_XNUM3; cubic(XN, k0, k1, k2, k3); }
+    { const Fp2 k0 = B200_FP2_ISO_YNUM0, k1 = B200_FP2_ISO_YNUM1, k2 = B200_FP2_ISO_YNUM2, k3 = B200_FP2_ISO_YNUM3; cubic(YN, k0, k1, k2, k3); }
+    { const Fp2 k0 = B200_FP2_ISO_YDEN0, k1 = B200_FP2_ISO_YDEN1, k2 = B200_FP2_ISO_YDEN2, k3 = B200_FP2_ISO_YDEN3; cubic(YD, k0, k1, k2, k3); }
+    {
+        const Fp2 k0 = B200_FP2_ISO_XDEN0, k1 = B200_FP2_ISO_XDEN1, k2 = B200_FP2_ISO_XDEN2;
+        Fp2 a;                                  // (k2 xn + k1 xd) xn + k0 xd^2
+        fp2_mul(XD, k2, xn); fp2_mul(a, k1, xd); fp2_add(XD, XD, a);
+        fp2_mul(XD, XD, xn); fp2_mul(a, k0, z2); fp2_add(XD, XD, a);
+    }
+    Fp2 zx, yd2;
+    fp2_mul(zx, xd, XD);                        // xd XD
+    fp2_mul(out.z, zx, YD);
+    fp2_sqr(yd2, YD);
+    fp2_mul(t, XN, zx);
+    fp2_mul(out.x, t, yd2);                     // X = XN (xd XD) YD^2
+    fp2_sqr(t, zx); fp2_mul(t, t, zx);          // (xd XD)^3
+    fp2_mul(t, t, yd2);
+    fp2_mul(t, t, YN);
+    fp2_mul(out.y, t, y);                       // Y = y YN (xd XD)^3 YD^2
+    if (fp2_is_zero(out.z)) jac_set_inf(out);
+}
+#define B200_SSWU_ISO(out, u) { Fp2 xn_, xd_, y_; sswu_map_frac(xn_, xd_, y_, u); iso3_map_frac(out, xn_, xd_, y_); }
+#else
+#define B200_SSWU_ISO(out, u) { Fp2 x_, y_; sswu_map(x_, y_, u); iso3_map(out, x_, y_); }
+#endif
+
 // first half, for j in {0, 1}: u_j = hash_to_field(msg)[j], Q_j = iso3(sswu(u_j)) in Jacobian coordinates
 B200_BIG void hash_to_g2_map(G2Jac& out, const uint8_t* msg, size_t len, int j) {
-    Fp2 u0, u1, x, y;
+    Fp2 u0, u1;
     hash_to_field_fp2(u0, u1, msg, len);
-    sswu_map(x, y, j ? u1 : u0);
-    iso3_map(out, x, y);
+    B200_SSWU_ISO(out, j ? u1 : u0);
 }
 // second half: Q_0 + Q_1, clear the cofactor, normalise
 B200_BIG void hash_to_g2_finish(G2Aff& out, const G2Jac& q0, const G2Jac& q1) {
@@ -163,13 +279,11 @@ B200_BIG void hash_to_g2_finish(G2Aff& out, const G2Jac& q0, const G2Jac& q1) {
 
 // full hash_to_curve -> affine G2 point
 B200_BIG void hash_to_g2(G2Aff& out, const uint8_t* msg, size_t len) {
-    Fp2 u0, u1, x, y;
+    Fp2 u0, u1;
     hash_to_field_fp2(u0, u1, msg, len);
     G2Jac q0, q1;
-    sswu_map(x, y, u0);
-    iso3_map(q0, x, y);
-    sswu_map(x, y, u1);
-    iso3_map(q1, x, y);
+    B200_SSWU_ISO(q0, u0);
+    B200_SSWU_ISO(q1, u1);
     jac_add(q0, q0, q1);
     g2_clear_cofactor(q1, q0);
     jac_to_aff(out, q1);

@@ -45,19 +45,30 @@ def engine():
     return _lib.init(int(os.environ.get("LOCAL_RANK", "0")))
 
 
-@pytest.fixture(scope="session")
-def host_math():
-    """The product's __host__ __device__ BLS math compiled for the CPU (tests/host_math/host_math.cpp)."""
+def _host_math_lib(suffix: str, defines):
     src = ROOT / "tests" / "host_math" / "host_math.cpp"
-    lib = ROOT / "tests" / "host_math" / "libhost_math.so"
+    lib = ROOT / "tests" / "host_math" / f"libhost_math{suffix}.so"
     deps = [src] + list((ROOT / "ethereum_consensus_b200" / "csrc").glob("*.cuh"))
     if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-o", str(lib), str(src)], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", *[f"-D{d}" for d in defines],
+                        "-o", str(lib), str(src)], check=True)
     L = ctypes.CDLL(str(lib))
     L.hm_fast_aggregate_verify.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
     L.hm_hash_to_g2.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     L.hm_hash_to_field.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
     return L
+
+
+@pytest.fixture(scope="session")
+def host_math():
+    """The product's __host__ __device__ BLS math compiled for the CPU (tests/host_math/host_math.cpp)."""
+    return _host_math_lib("", [])
+
+
+@pytest.fixture(scope="session")
+def host_math_sswu_fraction():
+    """Same, with the default-off A/B variant of the SSWU map (x kept as a fraction, no Fp2 inversion; h2c.cuh)."""
+    return _host_math_lib("_sswu_fraction", ["B200_SSWU_FRACTION"])
 
 
 @pytest.fixture(scope="session")
