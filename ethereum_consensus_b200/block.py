@@ -45,8 +45,15 @@ class SignatureSet:
 
     def add(self, site: str, pubkeys: Sequence[bytes], signing_root: bytes, signature: bytes, tolerant: bool = False,
             eth_variant: bool = False) -> None:
-        assert site in SITES and len(signing_root) == 32
-        self.entries.append(_Entry(site, [bytes(p) for p in pubkeys], bytes(signing_root), bytes(signature), tolerant, eth_variant))
+        if site not in SITES:
+            raise ValueError(f"unknown signature site {site!r}")
+        if len(signing_root) != 32:
+            raise ValueError("signing root must be 32 bytes")
+        # coerce through the byte newtypes (crypto/bls.rs:227-239,287-290): a wrong length would misalign the joined
+        # buffers of verify() and every later tuple with it
+        pks = [bytes(crypto.PublicKey(p)) for p in pubkeys]
+        sig = bytes(crypto.Signature(signature))
+        self.entries.append(_Entry(site, pks, bytes(signing_root), sig, tolerant, eth_variant))
 
     def add_indexed_attestation(self, site: str, validator_pubkeys, attesting_indices: Sequence[int], signing_root: bytes,
                                 signature: bytes) -> None:

@@ -159,11 +159,25 @@ def eth_aggregate_public_keys(public_keys: Sequence[PublicKey]) -> PublicKey:
 
 
 # ---- the throughput path ----------------------------------------------------------------------------------------
+def _nbytes(buf) -> int:
+    if hasattr(buf, "nbytes"):
+        return int(buf.nbytes)
+    if hasattr(buf, "numel"):
+        return int(buf.numel() * buf.element_size())
+    return len(buf)
+
+
 def fast_aggregate_verify_batch(pks_flat, pk_offsets, msgs32, sigs) -> np.ndarray:
     """T tuples at once -> int32 code per tuple (0 Ok, 5 InvalidSignature, 1/2/3/6 BLST decode errors).
     pks_flat: (sum K) x 48 bytes; pk_offsets: uint32[T+1]; msgs32: T x 32; sigs: T x 96 (host buffers)."""
     off = np.ascontiguousarray(pk_offsets, dtype=np.uint32)
     t = len(off) - 1
+    if t < 0 or (t >= 0 and int(off[0]) != 0):
+        raise ValueError("pk_offsets must hold T+1 entries starting at 0")
+    # the C side reads raw pointers: refuse buffers whose sizes disagree with the offsets
+    if _nbytes(pks_flat) != 48 * int(off[-1]) or _nbytes(msgs32) != 32 * t or _nbytes(sigs) != 96 * t:
+        raise ValueError(f"buffer sizes do not match the offsets: keys {_nbytes(pks_flat)} B for {int(off[-1])} keys, "
+                         f"msgs {_nbytes(msgs32)} B, sigs {_nbytes(sigs)} B for {t} tuples")
     out = np.empty(max(t, 1), dtype=np.int32)
     _lib.check(_lib.lib().b200_fast_aggregate_verify_batch(_lib.ptr(pks_flat), _lib.ptr(off), _lib.ptr(msgs32), _lib.ptr(sigs),
                                                            t, _lib.ptr(out)), "fast_aggregate_verify_batch")
@@ -188,6 +202,8 @@ class Registry:
         idx = np.ascontiguousarray(indices, dtype=np.uint32)
         off = np.ascontiguousarray(offsets, dtype=np.uint32)
         t = len(off) - 1
+        if t < 0 or len(idx) != int(off[-1]) or _nbytes(msgs32) != 32 * t or _nbytes(sigs) != 96 * t:
+            raise ValueError("indices / offsets / msgs / sigs sizes are inconsistent")
         out = np.empty(max(t, 1), dtype=np.int32)
         _lib.check(_lib.lib().b200_fast_aggregate_verify_batch_indexed(_lib.ptr(idx), _lib.ptr(off), _lib.ptr(msgs32),
                                                                        _lib.ptr(sigs), t, _lib.ptr(out)), "verify_batch_indexed")

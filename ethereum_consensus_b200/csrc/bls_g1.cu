@@ -27,7 +27,7 @@ __device__ __forceinline__ void g1_validate_body(const uint8_t* __restrict__ key
                                                  int32_t* __restrict__ codes) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint8_t b[48];
+    __align__(16) uint8_t b[48];  // written through uint4*
     const uint4* src = reinterpret_cast<const uint4*>(keys + size_t(i) * 48);
     uint4* dst = reinterpret_cast<uint4*>(b);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];

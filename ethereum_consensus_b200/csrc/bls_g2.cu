@@ -25,7 +25,7 @@ __global__ void B200_G2_BOUNDS k_g2_sig_decode(const uint8_t* __restrict__ sigs,
                                                        int32_t* __restrict__ sig_code) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint8_t b[96];
+    __align__(16) uint8_t b[96];  // written through uint4*
     const uint4* src = reinterpret_cast<const uint4*>(sigs + size_t(i) * 96);
     uint4* dst = reinterpret_cast<uint4*>(b);
 #pragma unroll

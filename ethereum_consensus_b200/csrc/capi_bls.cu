@@ -85,14 +85,36 @@ static int32_t check_ready(Engine& e) {
 }
 
 enum PairMode { MODE_FAST_AGGREGATE = 0, MODE_AGGREGATE = 1 };
+// message offsets travel as uint32 (32 bytes per tuple on the batch paths): 32 * T must not wrap
+constexpr size_t kMaxBatchTuples = size_t(1) << 26;
 
 // Core: `n_tuples` tuples.  MODE_FAST_AGGREGATE: tuple t sums keys [key_off[t], key_off[t+1]) and checks
 // e(sum, H(msg_t)) e(-g1, sig_t) == 1.  MODE_AGGREGATE: one tuple, pairs (key_i, H(msg_i)) + (-g1, sig).
 // keys: host bytes (strict) or nullptr with `index` (registry gather).  msgs: host bytes + offsets (n_msgs + 1).
+static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint8_t* keys, uint32_t n_keys,
+                               const uint32_t* index, uint32_t n_index, const uint32_t* key_off, const uint8_t* msgs,
+                               const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
+                               bool force_fail_shape, int32_t* out_codes);
+// An early error return must not leave work queued on the side streams (they read the caller's host buffers and the
+// engine's grow-only device buffers): drain all three before handing the error back.
 static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* keys, uint32_t n_keys,
                           const uint32_t* index, uint32_t n_index, const uint32_t* key_off, const uint8_t* msgs,
                           const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
                           bool force_fail_shape, int32_t* out_codes) {
+    const int32_t rc = run_verify_impl(e, s, mode, keys, n_keys, index, n_index, key_off, msgs, msg_off, n_msgs, sigs,
+                                       n_tuples, force_fail_shape, out_codes);
+    if (rc != B200_SUCCESS) {
+        cudaStreamSynchronize(e.stream);
+        cudaStreamSynchronize(s.sb);
+        cudaStreamSynchronize(s.sc);
+        cudaGetLastError();
+    }
+    return rc;
+}
+static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint8_t* keys, uint32_t n_keys,
+                               const uint32_t* index, uint32_t n_index, const uint32_t* key_off, const uint8_t* msgs,
+                               const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
+                               bool force_fail_shape, int32_t* out_codes) {
     const bool registry = (keys == nullptr && index != nullptr);
     const uint32_t T = n_tuples;
     const uint32_t n_g1 = (mode == MODE_FAST_AGGREGATE ? T : n_keys) + 1;  // + (-g1)
@@ -297,7 +319,7 @@ int32_t b200_fast_aggregate_verify_batch(const uint8_t* pks_flat, const uint32_t
     int32_t rc = check_ready(e);
     if (rc) return rc;
     if (n_tuples == 0) return B200_SUCCESS;
-    if (!pk_offsets || !msgs32 || !sigs || !out_codes || n_tuples > 0x3fffffffu) return B200_ERR_BAD_ARG;
+    if (!pk_offsets || !msgs32 || !sigs || !out_codes || n_tuples > kMaxBatchTuples) return B200_ERR_BAD_ARG;
     for (size_t t = 0; t < n_tuples; t++)
         if (pk_offsets[t] > pk_offsets[t + 1]) return B200_ERR_BAD_ARG;
     const uint32_t nk = pk_offsets[n_tuples];
@@ -357,7 +379,7 @@ int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indices, const 
     int32_t rc = check_ready(e);
     if (rc) return rc;
     if (n_tuples == 0) return B200_SUCCESS;
-    if (!offsets || !msgs32 || !sigs || !out_codes || n_tuples > 0x3fffffffu) return B200_ERR_BAD_ARG;
+    if (!offsets || !msgs32 || !sigs || !out_codes || n_tuples > kMaxBatchTuples) return B200_ERR_BAD_ARG;
     BlsState* s;
     rc = bls_state(e, &s);
     if (rc) return rc;
@@ -427,6 +449,11 @@ int32_t b200_aggregate_verify(const uint8_t* pks_flat, size_t n_pks, const uint8
     std::vector<uint32_t> moff(1, 0);
     std::vector<uint8_t> flat;
     if (!shape_fail) {
+        size_t total = 0;
+        for (size_t i = 0; i < n_msgs; i++) {
+            if (msg_lens[i] > 0xffffffffu - total) { e.last_error = "aggregate_verify: messages exceed 4 GiB in total"; return B200_ERR_BAD_ARG; }
+            total += msg_lens[i];
+        }
         for (size_t i = 0; i < n_msgs; i++) {
             flat.insert(flat.end(), msgs[i], msgs[i] + msg_lens[i]);
             moff.push_back(uint32_t(flat.size()));

@@ -173,6 +173,7 @@ int32_t b200_merkleize(const uint8_t* chunks, size_t n_chunks, uint64_t limit, u
     if (rc) return rc;
     if (!out || (!chunks && n_chunks)) return B200_ERR_BAD_ARG;
     if (limit == 0) limit = n_chunks ? n_chunks : 1;
+    if (limit > (uint64_t(1) << 63)) return B200_ERR_BAD_ARG;
     if (n_chunks > limit) return B200_ERR_LIMIT;
     SszPlan p;
     std::vector<uint32_t> outs{p.wide_chunks(p.stage_field(chunks, 32 * n_chunks), n_chunks, depth_for(limit))};
@@ -218,6 +219,7 @@ int32_t b200_htr_validators(const uint8_t* ssz, size_t n, uint64_t limit, uint8_
     if (rc) return rc;
     if (!out || (!ssz && n)) return B200_ERR_BAD_ARG;
     if (limit == 0) limit = n ? n : 1;
+    if (limit > (uint64_t(1) << 63)) return B200_ERR_BAD_ARG;
     if (n > limit) return B200_ERR_LIMIT;
     SszPlan p;
     uint32_t r = p.wide_records(JOB_VALIDATORS, p.stage_field(ssz, 121 * n), n, depth_for(limit));
@@ -234,6 +236,7 @@ int32_t b200_htr_packed(const uint8_t* data, size_t nbytes, uint64_t limit_chunk
     if (!out || (!data && nbytes)) return B200_ERR_BAD_ARG;
     uint64_t n = (nbytes + 31) / 32;
     if (limit_chunks == 0) limit_chunks = n ? n : 1;
+    if (limit_chunks > (uint64_t(1) << 63)) return B200_ERR_BAD_ARG;
     if (n > limit_chunks) return B200_ERR_LIMIT;
     SszPlan p;
     uint32_t r = p.wide_chunks(p.stage_field(data, nbytes), n, depth_for(limit_chunks));

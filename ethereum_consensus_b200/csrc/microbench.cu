@@ -2,6 +2,9 @@
 // runs on (MEASURED_PEAKS.json only carries HBM / bf16 figures).  kind 0: IMAD.WIDE.U32 (32x32+64, the Montgomery
 // multiply-add), kind 1: IMAD.U32 lo, kind 2: LOP3/SHF/IADD3 mix (the SHA-256 round ops), all dependency-limited
 // only by 8 independent chains per thread with the SMs fully occupied.
+// kind 7 / 8 (round 2): IMAD.WIDE.U32 whose multiplicand is the low word of ANOTHER chain's accumulator, multiplier in a
+// register (7) or an immediate (8), instead of the addend's own low word — kind 0 reads its 64-bit accumulator pair as BOTH a source and the addend, which the round-1
+// review showed saturates below the pipe's real issue rate (ncu sm__pipe_fmaheavy at 67 % while kind 0 said "peak").
 #include <cuda_runtime.h>
 
 #include "engine.h"
@@ -24,6 +27,10 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t iters, uint32_t seed,
             for (int k = 0; k < 8; k++) {
                 if (KIND == 0) {
                     acc[k] = uint64_t(uint32_t(acc[k])) * y + acc[k];                         // IMAD.WIDE.U32
+                } else if (KIND == 7) {
+                    acc[k] = uint64_t(uint32_t(acc[(k + 4) & 7])) * y + acc[k];
+                } else if (KIND == 8) {
+                    acc[k] = uint64_t(uint32_t(acc[(k + 4) & 7])) * 0xb9feffffu + acc[k];
                 } else if (KIND == 1) {
                     uint32_t lo = uint32_t(acc[k]);
                     lo = lo * y + uint32_t(acc[k] >> 32);                                        // IMAD
@@ -74,7 +81,7 @@ extern "C" int32_t b200_measure_int_peak(int32_t kind, double* gops) {
     Engine& e = engine();
     std::unique_lock<std::mutex> lk(e.mu);
     if (!e.ready) return B200_ERR_NOT_INITIALIZED;
-    if (!gops || kind < 0 || kind > 6) return B200_ERR_BAD_ARG;
+    if (!gops || kind < 0 || kind > 8) return B200_ERR_BAD_ARG;
     B200_CUDA_TRY(cudaSetDevice(e.device));
     int sms = 0;
     B200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e.device));
@@ -90,7 +97,9 @@ extern "C" int32_t b200_measure_int_peak(int32_t kind, double* gops) {
         else if (kind == 3) k_int_peak<3><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         else if (kind == 4) k_int_peak<4><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         else if (kind == 5) k_int_peak<5><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
-        else k_int_peak<6><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else if (kind == 6) k_int_peak<6><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else if (kind == 7) k_int_peak<7><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
+        else k_int_peak<8><<<blocks, threads, 0, e.stream>>>(iters, 1 + rep, d);
         e.launches++;
         B200_CUDA_TRY(cudaEventRecord(e.ev1, e.stream));
         B200_CUDA_TRY(cudaGetLastError());

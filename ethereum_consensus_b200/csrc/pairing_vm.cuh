@@ -4,11 +4,7 @@
 // Register allocation guarantees that no slot is both read and written in the same round.
 #pragma once
 #include "fp12.cuh"
-#if defined(B200_VM_TEAM16)  // A/B knob; measured on B200: teams of 8 lanes beat 16 (profiles/r1_tuning.md)
-#include "pairing_vm_prog16.cuh"
-#else
-#include "pairing_vm_prog.cuh"
-#endif
+#include "pairing_vm_prog.cuh"  // teams of 8 lanes (teams of 16 measured slower on B200: profiles/r1_tuning.md)
 
 namespace b200 {
 

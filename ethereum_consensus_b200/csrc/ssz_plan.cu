@@ -10,9 +10,11 @@ namespace b200 {
 static constexpr uint32_t kSmallBase = 65;
 static constexpr uint32_t kSmallCap = 8192;
 
+// smallest d with 2^d >= n; n above 2^63 saturates at 64 (the zero-subtree table has 65 levels, 0..64) — the shift
+// below never reaches 64, so an absurd caller-supplied limit can neither invoke undefined behaviour nor spin.
 int depth_for(uint64_t n) {
     int d = 0;
-    while ((uint64_t(1) << d) < n) d++;
+    while (d < 64 && (uint64_t(1) << d) < n) d++;
     return d;
 }
 

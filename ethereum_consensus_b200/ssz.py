@@ -160,6 +160,8 @@ def shard_roots(ssz, preset: str, rank: int, world: int) -> bytes:
 
 def combine_roots(ssz, preset: str, world: int, all_roots: bytes) -> bytes:
     nbytes = ssz.nbytes if hasattr(ssz, "nbytes") else len(ssz)
+    if world < 1 or len(all_roots) != world * 160:
+        raise ValueError(f"all_roots must hold world x 5 x 32 = {world * 160} bytes, got {len(all_roots)}")
     out = _out32()
     _rc(_lib.lib().b200_htr_beacon_state_deneb_combine(_lib.ptr(ssz), nbytes, _lib.PRESET[preset], world,
                                                        _lib.ptr(all_roots), out), "combine_roots")
