@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ.get("B200_LIB", PKG / "libb200_consensus.so"))  # B20
 SUCCESS, BAD_ENCODING, POINT_NOT_ON_CURVE, POINT_NOT_IN_GROUP = 0, 1, 2, 3
 AGGR_TYPE_MISMATCH, VERIFY_FAIL, PK_IS_INFINITY, BAD_SCALAR = 4, 5, 6, 7
 EMPTY_AGGREGATE = 16
-ERR_CUDA, ERR_NO_DEVICE, ERR_BAD_ARG, ERR_SSZ_MALFORMED, ERR_NOT_INITIALIZED, ERR_LIMIT = 0x100, 0x101, 0x102, 0x103, 0x104, 0x105
+ERR_CUDA, ERR_NO_DEVICE, ERR_BAD_ARG, ERR_SSZ_MALFORMED, ERR_NOT_INITIALIZED, ERR_LIMIT, ERR_COMM = 0x100, 0x101, 0x102, 0x103, 0x104, 0x105, 0x106
 PRESET = {"mainnet": 0, "minimal": 1}
 
 _u8p = C.POINTER(C.c_uint8)
@@ -56,6 +56,15 @@ _PROTOS = {
     "b200_state_root_incremental": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "b200_htr_beacon_state_deneb_shard": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b200_htr_beacon_state_deneb_combine": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    # multi-GPU (comm.cu): the exchange step lives inside the library
+    "b200_comm_unique_id": (C.c_int32, [C.c_void_p]),
+    "b200_comm_init": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "b200_comm_info": (C.c_int32, [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "b200_comm_destroy": (None, []),
+    "b200_collective_count": (C.c_uint64, []),
+    "b200_comm_all_gather_bytes": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200_htr_beacon_state_deneb_sharded": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
+    "b200_fast_aggregate_verify_batch_sharded": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 

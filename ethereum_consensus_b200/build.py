@@ -14,13 +14,14 @@ OBJ = PKG / "build"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
-# Per-TU ptxas optimisation level.  bls_g1.cu (the per-key kernel, 85 % of a strict step) is assembled at -O1: at the
-# default level ptxas interleaves more carry chains than it has predicate registers and spills the carries into a GPR
-# bitmask (13.3 k LOP3 + 1.8 k P2R + 1.8 k ISETP of 51 k instructions); at -O1 the same 19.4 k IMAD.WIDE remain, four
-# chains stay interleaved and the spill code is gone (34 k instructions, 120 B instead of 344 B of stack).
-# NOTE: switched after round 1's GPU budget was spent — the committed round-1 measurements are of the -O3 build;
-# `B200_PTXAS_OPT=bls_g1.cu:3` restores it (profiles/r1_tuning.md).  NVVM still runs at -O3.
-DEFAULT_PTXAS_OPT = {"bls_g1.cu": 1}
+# Per-TU ptxas optimisation level.  The three BLS translation units whose kernels are chains of inline-PTX Montgomery
+# products are assembled at -O1: at the default level ptxas interleaves more carry chains than it has predicate
+# registers and spills the carries into a GPR bitmask (bls_g1.cu: 13.3 k LOP3 + 1.8 k P2R + 1.8 k ISETP of 51 k
+# instructions); at -O1 the same IMAD.WIDE remain, four chains stay interleaved and the spill code is gone.
+# Measured on B200 (profiles/r2_ab_variants.txt, T=4096, K=512): per-key kernel 161.9 -> 136.0 ms (bls_g1.cu),
+# signature/message kernels 10.5 -> 7.5 ms (bls_g2.cu), Miller + final-exponentiation VM 15.96 -> 15.2 ms (bls_vm.cu).
+# `B200_PTXAS_OPT=bls_g1.cu:3` restores the default level for a TU.  NVVM still runs at -O3.
+DEFAULT_PTXAS_OPT = {"bls_g1.cu": 1, "bls_g2.cu": 1, "bls_vm.cu": 1}
 
 
 def _stale(target: Path, deps) -> bool:

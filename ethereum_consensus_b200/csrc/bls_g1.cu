@@ -5,9 +5,11 @@
 // k_g1_validate : one thread per key, Fp limbs in registers; 48 B in, 100 B out.  Integer-pipe bound.
 // k_g1_aggregate: one warp per tuple; lanes stride over the tuple's keys with mixed additions, then a
 //                 5-round shared-memory tree of Jacobian additions; lane 0 normalises to affine.
-// measured on B200 (profiles/r1_tuning.md): in this kernel the dedicated square's extra carry bookkeeping cancels its
-// 23 % fewer wide MADs, and inlined products beat by-value calls -> squares use the product, everything inlined.
-#ifndef B200_G1_PTX_SQR
+// Squarings (~75 % of this kernel's products) use the dedicated PTX square (222 wide MADs instead of 288).  Measured
+// on B200 at ptxas -O1 (profiles/r2_ab_variants.txt, 2^21 keys): 132.1 -> 128.2 ms with 256-thread CTAs at 224
+// registers; it LOSES with the 168-register cap (136.0 -> 143.2 ms: the square's wider live range spills) and lost at
+// ptxas' default level in round 1 (predicate spills).  -DB200_G1_SQR_VIA_MUL restores squares-by-product.
+#if defined(B200_G1_SQR_VIA_MUL)
 #define B200_FP_SQR_VIA_MUL 1
 #endif
 #if defined(B200_G1_CALL_MUL)  // A/B knob: by-value function calls instead of inlined products in the per-key kernel
@@ -36,10 +38,10 @@ __device__ __forceinline__ void g1_validate_body(const uint8_t* __restrict__ key
     codes[i] = rc;
     if (rc == BLS_SUCCESS) out[i] = p;
 }
-// Default (variant 7): 384-thread CTAs, one per SM, capped at 168 registers = 12 warps per SM.  Variant 0: 256 threads
-// at 224 registers (8 warps, no spills).  Measured on B200, 2^21 keys: 161.9 vs 164.5 ms — the kernel is bound by
-// fixed-latency dependency stalls on the FMA-heavy pipe (ncu: `wait` is the top stall), so a third warp per scheduler
-// buys more than the 344 B/thread of spills cost (__maxnreg__ cannot be combined with __launch_bounds__).
+// Default (variant 0): 256-thread CTAs at 224 registers (8 warps per SM, no spills).  Variant 7: 384 threads capped at
+// 168 registers = 12 warps per SM.  Measured on B200, 2^21 keys: at ptxas' default level 164.5 vs 161.9 ms (round 1,
+// variant 7 was the default); at -O1 the spill-free variant wins, 132.1 vs 136.0 ms, and 128.2 vs 143.2 ms with the
+// dedicated square (profiles/r2_ab_variants.txt).  (__maxnreg__ cannot be combined with __launch_bounds__.)
 __global__ void __maxnreg__(224) k_g1_validate_main(const uint8_t* __restrict__ keys, uint32_t n, G1Aff* __restrict__ out,
                                                     int32_t* __restrict__ codes) {
     g1_validate_body(keys, n, out, codes);
@@ -185,9 +187,9 @@ static size_t with_pow_tab(K kernel, unsigned threads) {
     if (n_seen < 16) seen[n_seen++] = key;
     return bytes;
 }
-// tuning knob (B200_G1_VARIANT): 7: 384 threads, 168 registers (default); 0: 256 threads, 224 registers;
+// tuning knob (B200_G1_VARIANT): 0: 256 threads, 224 registers (default); 7: 384 threads, 168 registers;
 // threads x min CTAs/SM = 1: 128x2, 2: 128x3, 3: 256x2, 4: 128x4, 5: 256x1 uncapped
-static int g_g1_variant = 7;
+static int g_g1_variant = 0;
 void set_g1_variant(int v) { if (v >= 0 && v <= 7) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;

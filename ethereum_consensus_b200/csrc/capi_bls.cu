@@ -9,11 +9,13 @@
 //   stream C: H2D msgs | K4 hash_to_G2 (2T + T threads)                   }
 //   stream A: K5 Miller loops (2T teams of 8 lanes) | K6 Gt product + final exponentiation (T teams) | D2H codes
 // Registry mode skips K1: validated affine keys stay resident in HBM and K2 gathers them by validator index.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "bls_kernels.cuh"
+#include "comm.h"
 #include "engine.h"
 
 namespace b200 {
@@ -21,7 +23,7 @@ namespace b200 {
 struct BlsState {
     cudaStream_t sb = nullptr, sc = nullptr;  // signatures / messages: run under the per-key kernel
     cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
-    DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp;
+    DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp, gath;
     PinnedBuf stage;
     G1Aff* d_negg1 = nullptr;
     G1Pre* d_negg1_pre = nullptr;
@@ -331,6 +333,55 @@ int32_t b200_fast_aggregate_verify_batch(const uint8_t* pks_flat, const uint32_t
     for (size_t t = 0; t <= n_tuples; t++) moff[t] = uint32_t(32 * t);
     return run_verify(e, *s, MODE_FAST_AGGREGATE, pks_flat, nk, nullptr, 0, pk_offsets, msgs32, moff.data(),
                       uint32_t(n_tuples), sigs, uint32_t(n_tuples), false, out_codes);
+}
+
+// BASELINE configs[4]: the batch sharded over the communicator's ranks; verdicts exchanged with one ncclAllGather.
+int32_t b200_fast_aggregate_verify_batch_sharded(const uint8_t* pks_flat, const uint32_t* pk_offsets, const uint8_t* msgs32,
+                                                 const uint8_t* sigs, size_t n_tuples, int32_t* out_codes) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    const Comm& c = comm();
+    if (!c.ready) { e.last_error = "b200_comm_init has not been called"; return B200_ERR_NOT_INITIALIZED; }
+    if (n_tuples == 0) return B200_SUCCESS;
+    if (!pk_offsets || !msgs32 || !sigs || !out_codes || n_tuples > kMaxBatchTuples) return B200_ERR_BAD_ARG;
+    for (size_t t = 0; t < n_tuples; t++)
+        if (pk_offsets[t] > pk_offsets[t + 1]) return B200_ERR_BAD_ARG;
+    if (pk_offsets[n_tuples] && !pks_flat) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    // contiguous block of tuples per rank, balanced to within one (parallel.tuple_shard in the Python mirror)
+    const size_t world = size_t(c.world), rank = size_t(c.rank);
+    const size_t base = n_tuples / world, rem = n_tuples % world;
+    const size_t lo = rank * base + std::min(rank, rem), cnt = base + (rank < rem ? 1 : 0);
+    const size_t per = base + (rem ? 1 : 0);  // padded shard length: equal contributions to the all-gather
+    B200_CUDA_TRY(s->out.reserve((per + 1) * 4));
+    B200_CUDA_TRY(s->gath.reserve(world * per * 4 + 16));
+    if (cnt) {
+        std::vector<uint32_t> koff(cnt + 1), moff(cnt + 1);
+        for (size_t t = 0; t <= cnt; t++) { koff[t] = pk_offsets[lo + t] - pk_offsets[lo]; moff[t] = uint32_t(32 * t); }
+        std::vector<int32_t> local(cnt);
+        rc = run_verify(e, *s, MODE_FAST_AGGREGATE, pks_flat ? pks_flat + size_t(pk_offsets[lo]) * 48 : nullptr, koff[cnt], nullptr, 0,
+                        koff.data(), msgs32 + 32 * lo, moff.data(), uint32_t(cnt), sigs + 96 * lo, uint32_t(cnt), false,
+                        local.data());
+        if (rc) return rc;
+    }
+    cudaStream_t sa = e.stream;
+    int32_t* d_out = static_cast<int32_t*>(s->out.p);
+    if (per > cnt) B200_CUDA_TRY(cudaMemsetAsync(d_out + cnt, 0xff, (per - cnt) * 4, sa));
+    rc = comm_all_gather(e, d_out, s->gath.p, per * 4, sa);   // the path's one exchange step
+    if (rc) return rc;
+    B200_CUDA_TRY(s->stage.reserve(world * per * 4 + 64));
+    B200_CUDA_TRY(cudaMemcpyAsync(s->stage.p, s->gath.p, world * per * 4, cudaMemcpyDeviceToHost, sa));
+    B200_CUDA_TRY(cudaStreamSynchronize(sa));
+    const int32_t* h = static_cast<const int32_t*>(s->stage.p);
+    for (size_t r = 0; r < world; r++) {
+        const size_t rlo = r * base + std::min(r, rem), rcnt = base + (r < rem ? 1 : 0);
+        memcpy(out_codes + rlo, h + r * per, rcnt * 4);
+    }
+    return B200_SUCCESS;
 }
 
 int32_t b200_registry_load(const uint8_t* pks_flat, size_t n) {

@@ -5,6 +5,7 @@
 #include <memory>
 #include <vector>
 
+#include "comm.h"
 #include "engine.h"
 #include "sha256.cuh"
 #include "ssz_plan.h"
@@ -467,6 +468,22 @@ int32_t b200_htr_beacon_state_deneb_combine(const uint8_t* ssz, size_t len, int3
     std::vector<uint32_t> outs;
     rc = build_beacon_state_combine_plan(p, ssz, len, preset, world, all_roots, outs);
     if (rc) return rc;
+    return run_oneshot(e, p, outs, out);
+}
+
+// One call, all ranks: slices + small fields -> ncclAllGather of 5 x 32 B on the engine stream -> finisher.
+int32_t b200_htr_beacon_state_deneb_sharded(const uint8_t* ssz, size_t len, int32_t preset, uint8_t out[32]) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!ssz || !out) return B200_ERR_BAD_ARG;
+    const Comm& c = comm();
+    if (!c.ready) { e.last_error = "b200_comm_init has not been called"; return B200_ERR_NOT_INITIALIZED; }
+    SszPlan p;
+    std::vector<uint32_t> outs;
+    rc = build_beacon_state_sharded_plan(p, ssz, len, preset, c.rank, c.world, outs);
+    if (rc) { e.last_error = "sharded hash_tree_root: malformed SSZ or world not a power of two"; return rc; }
     return run_oneshot(e, p, outs, out);
 }
 

@@ -52,10 +52,13 @@ struct Engine {
     std::mutex mu;
     std::string last_error;
     uint64_t launches = 0;
+    uint64_t collectives = 0;  // NCCL collectives issued by the library (comm.cu)
     float last_kernel_ms = 0.f;
     // SSZ scratch (one-shot calls)
     DevBuf arena, fields, planbuf;
     PinnedBuf staging;
+    DevBuf xch_dev;        // b200_comm_all_gather_bytes scratch
+    PinnedBuf xch_host;
     uint32_t* d_zero = nullptr;  // 65 zero-subtree hashes, word form
     // BLS scratch lives in bls_engine (opaque here)
     void* bls = nullptr;

@@ -236,8 +236,8 @@ __global__ void k_scatter_elements(uint8_t* __restrict__ dst, const uint64_t* __
 
 // Single-CTA finisher: executes the planner's op list wave by wave (all ops of a wave are independent).
 __global__ void __launch_bounds__(kFinisherThreads) k_merkle_finisher(uint32_t* arena, const FinOp* ops,
-                                                                        const uint32_t* wave_end, int nwaves) {
-    uint32_t begin = 0;
+                                                                        const uint32_t* wave_end, int nwaves, uint32_t first_op) {
+    uint32_t begin = first_op;
 #pragma unroll 1
     for (int w = 0; w < nwaves; w++) {
         const uint32_t end = wave_end[w];
@@ -246,6 +246,10 @@ __global__ void __launch_bounds__(kFinisherThreads) k_merkle_finisher(uint32_t* 
             const FinOp op = ops[i];
             uint32_t l[8], r[8], out[8];
             load_node(arena + uint64_t(op.a) * 8, l);
+            if (op.kind == FIN_COPY) {
+                store_node(arena + uint64_t(op.dst) * 8, l);
+                continue;
+            }
             load_node(arena + uint64_t(op.b) * 8, r);
             hash_pair_words(l, r, out);
             store_node(arena + uint64_t(op.dst) * 8, out);
@@ -298,9 +302,9 @@ void launch_scatter(uint8_t* dst, const uint64_t* idx, const uint8_t* vals, uint
     k_scatter_elements<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, idx, vals, n, elem);
 }
 
-void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream) {
+void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream, uint32_t first_op) {
     if (nwaves == 0) return;
-    k_merkle_finisher<<<1, kFinisherThreads, 0, static_cast<cudaStream_t>(stream)>>>(arena, ops, wave_end, nwaves);
+    k_merkle_finisher<<<1, kFinisherThreads, 0, static_cast<cudaStream_t>(stream)>>>(arena, ops, wave_end, nwaves, first_op);
 }
 
 }  // namespace b200

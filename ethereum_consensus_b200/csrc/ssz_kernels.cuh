@@ -34,10 +34,12 @@ struct StageDesc {
     const uint32_t* zero_nodes;  // device: zero-subtree hashes, word form, 65 x 8 words
 };
 
-// finisher op: arena[dst] = H(arena[a] || arena[b]); indices are node indices into the arena
+// finisher op: arena[dst] = H(arena[a] || arena[b]) (kind 0) or arena[dst] = arena[a] (kind 1: gathers nodes into the
+// contiguous send region of a multi-GPU exchange); indices are node indices into the arena
 struct FinOp {
-    uint32_t a, b, dst, pad_;
+    uint32_t a, b, dst, kind;
 };
+enum FinKind : uint32_t { FIN_HASH = 0, FIN_COPY = 1 };
 
 constexpr int kFinisherThreads = 1024;
 constexpr int kMaxWaves = 256;
@@ -48,6 +50,7 @@ void launch_stage(const StageDesc& sd, void* stream);
 // dirty-path variants: thread t handles output sel[t] (JOB_VALIDATORS or JOB_REDUCE only)
 void launch_sparse(const Job& jb, const uint32_t* zero_nodes, const uint32_t* sel, uint32_t n_sel, void* stream);
 void launch_scatter(uint8_t* dst, const uint64_t* idx, const uint8_t* vals, uint32_t n, uint32_t elem, void* stream);
-void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream);
+// waves [0, nwaves) of `wave_end` (cumulative op counts); the first wave starts at op `first_op`
+void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream, uint32_t first_op = 0);
 
 }  // namespace b200

@@ -1,5 +1,6 @@
 // Host planner + executor for device-side SSZ hash_tree_root (see ssz_plan.h).
 #include "ssz_plan.h"
+#include "comm.h"
 
 #include <cstdlib>
 
@@ -45,10 +46,23 @@ int SszPlan::ready_wave(uint32_t idx) const {
 uint32_t SszPlan::hash2(uint32_t a, uint32_t b) {
     uint32_t dst = uint32_t(arena_alloc(1));
     int w = std::max(ready_wave(a), ready_wave(b));
-    ops_.push_back(FinOp{a, b, dst, 0});
+    ops_.push_back(FinOp{a, b, dst, FIN_HASH});
     op_wave_.push_back(w);
     ready_[dst] = w + 1;
     return dst;
+}
+uint32_t SszPlan::exchange(const std::vector<uint32_t>& local, int world) {
+    xch_n_ = uint32_t(local.size());
+    xch_world_ = world;
+    xch_send_ = uint32_t(arena_alloc(xch_n_));
+    xch_recv_ = uint32_t(arena_alloc(uint64_t(xch_n_) * uint64_t(world)));
+    for (uint32_t i = 0; i < xch_n_; i++) {   // gather the local nodes into the contiguous send region
+        const int w = ready_wave(local[i]);
+        ops_.push_back(FinOp{local[i], local[i], xch_send_ + i, FIN_COPY});
+        op_wave_.push_back(w);
+    }
+    for (uint32_t i = 0; i < xch_n_ * uint32_t(world); i++) ready_[xch_recv_ + i] = kRemoteWave;
+    return xch_recv_;
 }
 uint32_t SszPlan::merkle_small(std::vector<uint32_t> nodes, int level, int depth_target) {
     if (nodes.empty()) return zero(depth_target);
@@ -151,7 +165,7 @@ int32_t ensure_zero_nodes(Engine& e) {
     B200_CUDA_TRY(cudaMemsetAsync(d, 0, 65 * 32, e.stream));
     std::vector<FinOp> ops(64);
     std::vector<uint32_t> wend(64);
-    for (uint32_t i = 0; i < 64; i++) { ops[i] = FinOp{i, i, i + 1, 0}; wend[i] = i + 1; }
+    for (uint32_t i = 0; i < 64; i++) { ops[i] = FinOp{i, i, i + 1, FIN_HASH}; wend[i] = i + 1; }
     FinOp* dops = nullptr; uint32_t* dw = nullptr;
     B200_CUDA_TRY(cudaMalloc(&dops, sizeof(FinOp) * 64));
     B200_CUDA_TRY(cudaMalloc(&dw, 4 * 64));
@@ -180,14 +194,23 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     uint32_t* d_arena = static_cast<uint32_t*>(arena.p);
     uint8_t* d_fields = static_cast<uint8_t*>(fields.p);
 
-    // order finisher ops by wave
-    int nwaves = 0;
-    for (int w : op_wave_) nwaves = std::max(nwaves, w + 1);
+    // order finisher ops by wave; ops that depend on a remote node (wave >= kRemoteWave) form pass 2, numbered after
+    // the local waves so that one cumulative wave_end table serves both finisher launches
+    int n_local_waves = 0, n_remote_waves = 0;
+    for (int w : op_wave_) {
+        if (w >= kRemoteWave) n_remote_waves = std::max(n_remote_waves, w - kRemoteWave + 1);
+        else n_local_waves = std::max(n_local_waves, w + 1);
+    }
+    if (xch_n_ && sparse) return B200_ERR_BAD_ARG;
+    if (n_remote_waves && !xch_n_) return B200_ERR_BAD_ARG;
+    std::vector<int> wave_of(op_wave_);   // (a resident plan runs many times: never renumber op_wave_ itself)
+    for (int& w : wave_of) if (w >= kRemoteWave) w = n_local_waves + (w - kRemoteWave);
+    const int nwaves = n_local_waves + n_remote_waves;
     std::vector<uint32_t> order(ops_.size());
     for (size_t i = 0; i < order.size(); i++) order[i] = uint32_t(i);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return op_wave_[a] < op_wave_[b]; });
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return wave_of[a] < wave_of[b]; });
     std::vector<uint32_t> wave_end(size_t(nwaves), 0);
-    for (size_t i = 0; i < order.size(); i++) wave_end[size_t(op_wave_[order[i]])] = uint32_t(i + 1);
+    for (size_t i = 0; i < order.size(); i++) wave_end[size_t(wave_of[order[i]])] = uint32_t(i + 1);
     for (int w = 1; w < nwaves; w++) wave_end[size_t(w)] = std::max(wave_end[size_t(w)], wave_end[size_t(w - 1)]);
 
     // dirty-path selection lists (host only): per chain, the outputs of job k that lie above the dirty inputs of job k
@@ -264,7 +287,10 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
             if (!c.validators || validator_jobs_.size() != 1 || copy != COPY_ALL) continue;
             const PJob& pj = validator_jobs_[0];
             const uint64_t n = pj.n_in;
-            const uint64_t per = ((n + 15) / 16 + kStageThreads - 1) / kStageThreads * kStageThreads;  // whole CTAs per slice
+            // up to 16 slices, none smaller than 32 768 records (a multi-GPU shard is 1/world of the list: slices that
+            // cannot fill the 148 SMs would cost more in launches than the overlap buys)
+            const uint64_t n_slices = std::min<uint64_t>(16, std::max<uint64_t>(1, n / 32768));
+            const uint64_t per = ((n + n_slices - 1) / n_slices + kStageThreads - 1) / kStageThreads * kStageThreads;  // whole CTAs per slice
             int k = 0;
             for (uint64_t lo = 0; lo < n; lo += per, k++) {
                 const uint64_t cnt = std::min(per, n - lo);
@@ -331,10 +357,21 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         }
     }
     if (trace) cudaEventRecord(tev[2], s);
-    if (nwaves) {
+    if (n_local_waves) {
         launch_finisher(d_arena, reinterpret_cast<const FinOp*>(d_plan + off_ops),
-                        reinterpret_cast<const uint32_t*>(d_plan + off_wend), nwaves, s);
+                        reinterpret_cast<const uint32_t*>(d_plan + off_wend), n_local_waves, s);
         e.launches++;
+    }
+    if (xch_n_) {   // the path's one exchange step, on the engine stream: slice roots -> every rank
+        if (comm().world != xch_world_) { e.last_error = "ssz plan: communicator size changed"; return B200_ERR_BAD_ARG; }
+        rc = comm_all_gather(e, d_arena + uint64_t(xch_send_) * 8, d_arena + uint64_t(xch_recv_) * 8, size_t(xch_n_) * 32, s);
+        if (rc) return rc;
+        if (n_remote_waves) {
+            launch_finisher(d_arena, reinterpret_cast<const FinOp*>(d_plan + off_ops),
+                            reinterpret_cast<const uint32_t*>(d_plan + off_wend) + n_local_waves, n_remote_waves, s,
+                            n_local_waves ? wave_end[size_t(n_local_waves - 1)] : 0u);
+            e.launches++;
+        }
     }
     B200_CUDA_TRY(cudaEventRecord(e.ev1, s));
     B200_CUDA_TRY(cudaGetLastError());
@@ -544,6 +581,45 @@ int32_t build_beacon_state_shard_plan(SszPlan& p, const uint8_t* s, size_t len, 
         size_t b0 = std::min(nb, size_t(first) * 32), b1 = std::min(nb, size_t(first + count) * 32);
         outputs.push_back(p.wide_chunks(p.stage_field(s + so.var[idx[q]] + b0, b1 - b0), count, k));
     }
+    return B200_SUCCESS;
+}
+
+// One plan for the fused multi-GPU call: this rank's slices of the five big lists, ALL small fields, one exchange of
+// the 5 slice roots, then the tops of the five lists and the 28-field tree on every rank.
+int32_t build_beacon_state_sharded_plan(SszPlan& p, const uint8_t* s, size_t len, int preset, int rank, int world,
+                                        std::vector<uint32_t>& outputs) {
+    StateOffsets so;
+    if (!parse_beacon_state(s, len, preset, so)) return B200_ERR_SSZ_MALFORMED;
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return B200_ERR_BAD_ARG;
+    const Preset& P = kPresets[preset];
+    auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
+    const int d_reg = depth_for(P.validator_registry_limit);
+    const uint64_t n_elems[5] = {sz(2) / 121, (sz(3) + 31) / 32, (sz(4) + 31) / 32, (sz(5) + 31) / 32, (sz(6) + 31) / 32};
+    const uint64_t lens[5] = {sz(2) / 121, sz(3) / 8, sz(4), sz(5), sz(6) / 8};
+    const int depth[5] = {d_reg, d_reg - 2, d_reg - 5, d_reg - 5, d_reg - 2};
+    const int var_of[5] = {2, 3, 4, 5, 6};
+    std::vector<uint32_t> local(5);
+    int kq[5];
+    for (int q = 0; q < 5; q++) {
+        uint64_t first, count;
+        slice_of(n_elems[q], world, rank, &first, &count, &kq[q]);
+        if (kq[q] > depth[q]) return B200_ERR_LIMIT;
+        if (q == 0) {
+            local[0] = p.wide_records(JOB_VALIDATORS, p.stage_field(s + so.var[2] + 121 * first, 121 * count), count, kq[0]);
+        } else {   // chunk-granular slices: starts are multiples of 2^k chunks => 32-byte aligned
+            const size_t nb = sz(var_of[q]);
+            const size_t b0 = std::min(nb, size_t(first) * 32), b1 = std::min(nb, size_t(first + count) * 32);
+            local[size_t(q)] = p.wide_chunks(p.stage_field(s + so.var[var_of[q]] + b0, b1 - b0), count, kq[q]);
+        }
+    }
+    const uint32_t remote = p.exchange(local, world);
+    uint32_t big[5];
+    for (int q = 0; q < 5; q++) {
+        std::vector<uint32_t> nodes;
+        for (int r = 0; r < world; r++) nodes.push_back(remote + uint32_t(r) * 5u + uint32_t(q));
+        big[q] = p.mix_in_length(p.merkle_small(nodes, kq[q], depth[q]), lens[q]);
+    }
+    outputs.assign(1, assemble_state(p, s, so, P, big));
     return B200_SUCCESS;
 }
 

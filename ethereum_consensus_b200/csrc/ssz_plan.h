@@ -61,6 +61,10 @@ public:
     uint32_t leaf_bytes(const uint8_t* p, size_t n);     // n <= 32, right-padded
     uint32_t hash2(uint32_t a, uint32_t b);              // finisher op
     uint32_t mix_in_length(uint32_t root, uint64_t len) { return hash2(root, leaf_u64(len)); }
+    // ---- multi-GPU exchange (one per plan): `n` local nodes are gathered into a contiguous send region by the last
+    // wave of finisher pass 1, one all-gather fills world x n remote nodes, and every op that depends on a remote node
+    // runs in finisher pass 2.  Returns the first remote node; rank r's copy of local[i] is remote + r*n + i.
+    uint32_t exchange(const std::vector<uint32_t>& local, int world);
     // root (at `depth_target`) of explicit nodes sitting at `level`
     uint32_t merkle_small(std::vector<uint32_t> nodes, int level, int depth_target);
     // container of small field roots
@@ -94,6 +98,7 @@ public:
                 const std::vector<uint32_t>& outputs, uint8_t* out,
                 const std::vector<std::vector<uint32_t>>* dirty = nullptr, DevBuf* selbuf = nullptr,
                 const std::vector<std::pair<const uint8_t*, const uint8_t*>>* changed_host_ranges = nullptr);
+    bool has_exchange() const { return xch_n_ != 0; }
 
     size_t field_bytes() const { return field_next_; }
     uint64_t arena_nodes() const { return arena_next_; }
@@ -113,6 +118,10 @@ private:
     std::vector<HostCopy> copies_;
     std::vector<PChain> chains_;
     int cur_chain_ = -1;
+    // exchange(): send region, receive region, nodes per rank, world
+    uint32_t xch_send_ = 0, xch_recv_ = 0, xch_n_ = 0;
+    int xch_world_ = 0;
+    static constexpr int kRemoteWave = 1 << 20;  // readiness wave of a remote node: splits the finisher in two passes
     uint64_t arena_next_ = 65 + 8192;  // [0,65) zero hashes, [65, 65+8192) small leaves uploaded with the plan
     size_t field_next_ = 0;
 
@@ -136,6 +145,8 @@ bool parse_beacon_state(const uint8_t* ssz, size_t len, int preset, StateOffsets
 int32_t build_beacon_state_plan(SszPlan& plan, const uint8_t* ssz, size_t len, int preset, std::vector<uint32_t>& outputs);
 int32_t build_beacon_state_shard_plan(SszPlan& plan, const uint8_t* ssz, size_t len, int preset, int rank, int world,
                                       std::vector<uint32_t>& outputs);
+int32_t build_beacon_state_sharded_plan(SszPlan& plan, const uint8_t* ssz, size_t len, int preset, int rank, int world,
+                                        std::vector<uint32_t>& outputs);
 int32_t build_beacon_state_combine_plan(SszPlan& plan, const uint8_t* ssz, size_t len, int preset, int world,
                                         const uint8_t* all_roots, std::vector<uint32_t>& outputs);
 

@@ -5,8 +5,15 @@
 * SSZ: rank r hashes its power-of-two-aligned slice of the five big BeaconState lists, one all_gather of 5 x 32 bytes
   per rank, then every rank finishes the tree (zero-hash padding, length mix-ins, small fields, 28-field top tree).
 
-The collective backend is whatever `torch.distributed` was initialised with: NCCL over NVLink on the GPUs, gloo in the
-CPU tests (tests/test_parallel_gloo.py) which inject oracle stand-ins for the two device calls.
+Two layers:
+* `comm_init` / `sharded_state_root` / `sharded_verify_batch` bind the library's own multi-GPU entry points
+  (include/b200_consensus.h "multi-GPU"): the NCCL exchange is issued by the C library on its engine stream, one C-ABI
+  call per rank, nothing in Python between "hash my slice" and "finish the tree".  This is what a Rust host binds.
+  The 128-byte NCCL id is moved between the ranks by whatever the host has (here: torch.distributed's store / a
+  broadcast); it is bootstrap only, never on the data path.
+* the older helpers below (`sharded_beacon_state_root`, `sharded_fast_aggregate_verify`) do the same exchange through
+  `torch.distributed` around the two-call shard/combine C ABI; they remain for hosts without NCCL and for the CPU
+  tests (tests/test_parallel_gloo.py: gloo, oracle stand-ins for the two device calls).
 """
 from __future__ import annotations
 
@@ -39,6 +46,76 @@ def tuple_shard(n_tuples: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+# ------------------------------------------------------------------------------------------------ library-side exchange
+def comm_init(rank: int = None, world: int = None) -> None:
+    """Create the library's communicator for this process.  With torch.distributed initialised the NCCL id travels by
+    `broadcast_object_list` (gloo or nccl, bootstrap only); a single process needs neither."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.lib()
+    dist = _dist()
+    if rank is None or world is None:
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        else:
+            rank, world = 0, 1
+    ident = (C.c_uint8 * 128)()
+    if world > 1:
+        box = [None]
+        if rank == 0:
+            _lib.check(lib.b200_comm_unique_id(ident), "comm_unique_id")
+            box[0] = bytes(ident)
+        dist.broadcast_object_list(box, src=0)
+        C.memmove(ident, box[0], 128)
+    _lib.check(lib.b200_comm_init(ident, rank, world), "comm_init")
+
+
+def comm_info():
+    import ctypes as C
+    from . import _lib
+    r, w, v = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    _lib.check(_lib.lib().b200_comm_info(C.byref(r), C.byref(w), C.byref(v)), "comm_info")
+    return int(r.value), int(w.value), int(v.value)
+
+
+def comm_destroy() -> None:
+    from . import _lib
+    _lib.lib().b200_comm_destroy()
+
+
+def comm_all_gather_codes(local_codes: np.ndarray) -> np.ndarray:
+    """Equal-length per-rank int32 verdict vectors -> rank-major concatenation, exchanged by the library (NCCL)."""
+    from . import _lib
+    _r, world, _v = comm_info()
+    loc = np.ascontiguousarray(local_codes, dtype=np.int32)
+    out = np.empty(world * len(loc), dtype=np.int32)
+    _lib.check(_lib.lib().b200_comm_all_gather_bytes(_lib.ptr(loc), loc.nbytes, _lib.ptr(out)), "comm_all_gather_bytes")
+    return out
+
+
+def sharded_state_root(ssz_bytes, preset: str = "mainnet") -> bytes:
+    """hash_tree_root(BeaconState) by all ranks, one C-ABI call per rank (b200_htr_beacon_state_deneb_sharded)."""
+    import ctypes as C
+    from . import _lib
+    nbytes = ssz_bytes.nbytes if hasattr(ssz_bytes, "nbytes") else len(ssz_bytes)
+    out = (C.c_uint8 * 32)()
+    _lib.check(_lib.lib().b200_htr_beacon_state_deneb_sharded(_lib.ptr(ssz_bytes), nbytes, _lib.PRESET[preset], out),
+               "htr_beacon_state_deneb_sharded")
+    return bytes(out)
+
+
+def sharded_verify_batch(pks_flat, pk_offsets, msgs32, sigs) -> np.ndarray:
+    """All T verdicts on every rank; each rank verifies tuple_shard(T, world, rank) (…_verify_batch_sharded)."""
+    from . import _lib
+    off = np.ascontiguousarray(pk_offsets, dtype=np.uint32)
+    t = len(off) - 1
+    out = np.empty(max(t, 1), dtype=np.int32)
+    _lib.check(_lib.lib().b200_fast_aggregate_verify_batch_sharded(_lib.ptr(pks_flat), _lib.ptr(off), _lib.ptr(msgs32), _lib.ptr(sigs),
+                                                                   t, _lib.ptr(out)), "fast_aggregate_verify_batch_sharded")
+    return out[:t]
+
+
+# ------------------------------------------------------------------------------------------------ torch.distributed exchange
 def _dist():
     import torch.distributed as dist
     return dist

@@ -47,7 +47,8 @@ enum {
     B200_ERR_BAD_ARG = 0x102,
     B200_ERR_SSZ_MALFORMED = 0x103, /* offsets / lengths inconsistent with the container schema */
     B200_ERR_NOT_INITIALIZED = 0x104,
-    B200_ERR_LIMIT = 0x105          /* more chunks than the declared limit (MerkleizationError) */
+    B200_ERR_LIMIT = 0x105,         /* more chunks than the declared limit (MerkleizationError) */
+    B200_ERR_COMM = 0x106           /* NCCL missing / communicator failure (multi-GPU entry points) */
 };
 
 enum { B200_PRESET_MAINNET = 0, B200_PRESET_MINIMAL = 1 };
@@ -120,6 +121,38 @@ B200_API int32_t b200_htr_beacon_state_deneb_shard(const uint8_t* ssz, size_t le
                                           uint8_t* out_roots /* 5*32 */);
 B200_API int32_t b200_htr_beacon_state_deneb_combine(const uint8_t* ssz, size_t len, int32_t preset, int32_t world,
                                             const uint8_t* all_roots /* world*5*32 */, uint8_t out[32]);
+
+/* ---- multi-GPU: one process per GPU, the exchange step lives INSIDE the library (SURVEY.md §8b `b200_init(n_gpus)`,
+ * §8e).  The reference is single-process (no counterpart); a Rust host with one process per GPU calls:
+ *   rank 0:   b200_comm_unique_id(id)  -> ships the 128 bytes to the other ranks by any means it likes (pipe, file, TCP)
+ *   all ranks: b200_init(local_gpu); b200_comm_init(id, rank, world)       (collective; NCCL over NVLink / NVSwitch)
+ * and then the *_sharded entry points below, which every rank must call with the same arguments.  world == 1 is
+ * legal (no NCCL needed) and makes the sharded calls equivalent to the single-GPU ones. */
+#define B200_COMM_ID_BYTES 128
+B200_API int32_t b200_comm_unique_id(uint8_t out_id[B200_COMM_ID_BYTES]);
+B200_API int32_t b200_comm_init(const uint8_t id[B200_COMM_ID_BYTES], int32_t rank, int32_t world);
+B200_API int32_t b200_comm_info(int32_t* rank, int32_t* world, int32_t* nccl_version);
+B200_API void b200_comm_destroy(void);
+/* all-gather of `bytes_per_rank` host bytes per rank into recv[world * bytes_per_rank] (rank-major): for the host's own
+ * small exchanges, e.g. verdict vectors when every rank verified a different batch (weak scaling). */
+B200_API int32_t b200_comm_all_gather_bytes(const uint8_t* send, size_t bytes_per_rank, uint8_t* recv);
+/* NCCL collectives issued by the library since start-up (bench.py reports it next to gpu_launches). */
+B200_API uint64_t b200_collective_count(void);
+
+/* hash_tree_root(deneb::BeaconState) computed by all ranks of the communicator in ONE call (deneb/spec/mod.rs:3215,3288):
+ * every rank passes the same serialization, uploads and hashes only its power-of-two-aligned slice of the five big
+ * lists (parallel H2D over every GPU's own PCIe link) together with all small fields, the 5 x 32-byte slice roots are
+ * exchanged with one ncclAllGather on the engine stream, and the finisher completes the tree on every rank: no host
+ * round trip between the phases.  world must be a power of two.  Every rank gets the same `out`. */
+B200_API int32_t b200_htr_beacon_state_deneb_sharded(const uint8_t* ssz, size_t len, int32_t preset, uint8_t out[32]);
+
+/* b200_fast_aggregate_verify_batch over all ranks (BASELINE configs[4]: an epoch's attestation batch sharded over
+ * 8 GPUs): every rank passes the same T tuples, verifies the contiguous block parallel.tuple_shard(T, world, rank)
+ * names (only that block's keys cross PCIe), and one ncclAllGather of the int32 verdicts leaves all T codes in
+ * `out_codes` on every rank — what process_block needs to pick the first failure. */
+B200_API int32_t b200_fast_aggregate_verify_batch_sharded(const uint8_t* pks_flat, const uint32_t* pk_offsets,
+                                                          const uint8_t* msgs32, const uint8_t* sigs, size_t n_tuples,
+                                                          int32_t* out_codes);
 
 /* ---- BLS12-381 signatures, min-pk (replaces the blst calls of crypto/bls.rs) ------------------------- */
 /* Public keys are 48-byte and signatures 96-byte ZCash-compressed points (crypto/bls.rs:23-25,227-239,287-290);
