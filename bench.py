@@ -139,57 +139,7 @@ class ClockSampler:
                 "reasons": [k for k, v in names.items() if bits & v]}
 
 
-# ------------------------------------------------------------------------------------------------ BLS workload
-def make_bls_workload(orc, T: int, K: int, rank: int, n_distinct: int = 1 << 15, n_registry: int = 1 << 20, threads: int = 8):
-    """registry of 2**20 validators (n_distinct distinct keys tiled), T tuples of K signers drawn
-    by a seeded permutation, 32-byte signing roots, aggregate signatures; ~3 % adversarial tuples."""
-    sk0 = int.from_bytes(hashlib.sha256(b"b200/sk0" + SEED.to_bytes(8, "little")).digest(), "big") % R_ORDER
-    delta = int.from_bytes(hashlib.sha256(b"b200/delta" + SEED.to_bytes(8, "little")).digest(), "big") % R_ORDER
-    keys = np.empty((n_distinct, 48), dtype=np.uint8)
-    orc.orc_pk_sequence(sk0.to_bytes(32, "big"), delta.to_bytes(32, "big"), n_distinct, keys.ctypes.data)
-    rng = np.random.default_rng(SEED + 1000 * rank)
-    perm = rng.permutation(n_registry).astype(np.uint32)
-    need = T * K
-    idx = np.resize(perm, need).astype(np.uint32)  # every validator attests need / n_registry times
-    off = (np.arange(T + 1, dtype=np.uint64) * K).astype(np.uint32)
-    msgs = np.frombuffer(b"".join(hashlib.sha256(b"b200/msg" + SEED.to_bytes(8, "little") + (rank << 32 | t).to_bytes(8, "little")).digest()
-                                  for t in range(T)), dtype=np.uint8).copy().reshape(T, 32)
-    kd = (idx % n_distinct).reshape(T, K).astype(object)
-    kind = np.zeros(T, dtype=np.int32)  # 0 valid, 1 wrong msg, 2 signer missing, 3 sig not in group, 4 pk infinity, 5 keys cancel
-    u = rng.random(T)
-    kind[u < 0.01] = 1
-    kind[(u >= 0.01) & (u < 0.02)] = 2
-    kind[(u >= 0.02) & (u < 0.025)] = 3
-    kind[(u >= 0.025) & (u < 0.0275)] = 4
-    kind[(u >= 0.0275) & (u < 0.03)] = 5
-    if K < 2:
-        kind[kind == 5] = 1  # a cancelling pair needs two keys
-    sks = np.empty((T, 32), dtype=np.uint8)
-    for t in range(T):
-        row = kd[t]
-        s = (K * sk0 + delta * int(row.sum())) % R_ORDER
-        if kind[t] == 2:
-            s = (s - (sk0 + delta * int(row[-1]))) % R_ORDER
-        sks[t] = np.frombuffer((s if s else 1).to_bytes(32, "big"), dtype=np.uint8)
-    sign_msgs = msgs.copy()
-    sign_msgs[kind == 1] ^= 0x55  # signature made over a different root
-    sigs = np.empty((T, 96), dtype=np.uint8)
-    orc.orc_sign_batch(sks.ctypes.data, sign_msgs.ctypes.data, T, sigs.ctypes.data, threads)
-    cases = json.loads((ROOT / "tests" / "golden" / "bls_cases.json").read_text())["fast_aggregate_verify"]
-    bad_sig = next(bytes.fromhex(c["sig"]) for c in cases if c["name"] == "signature not in subgroup")
-    sigs[kind == 3] = np.frombuffer(bad_sig, dtype=np.uint8)
-    flat = keys[idx % n_distinct].reshape(T, K, 48).copy()
-    inf_pk = np.zeros(48, dtype=np.uint8); inf_pk[0] = 0xC0
-    for t in np.nonzero(kind == 4)[0]:
-        flat[t, K // 3] = inf_pk
-    for t in np.nonzero(kind == 5)[0]:  # K/2 pairs (P, -P): the aggregate key is the point at infinity
-        half = flat[t, : K // 2].copy()
-        neg = half.copy(); neg[:, 0] ^= 0x20
-        flat[t, : K // 2] = half; flat[t, K // 2: 2 * (K // 2)] = neg
-    expect = np.select([kind == 0, kind == 4], [0, 6], default=5).astype(np.int32)
-    registry = np.tile(keys, (n_registry // n_distinct, 1))
-    return {"pks": flat.reshape(-1), "off": off, "msgs": msgs.reshape(-1), "sigs": sigs.reshape(-1), "expect": expect, "kind": kind,
-            "idx": idx, "registry": registry.reshape(-1), "T": T, "K": K}
+from tests.workloads import make_bls_workload  # noqa: E402  (the workload generator is shared with the parity tests)
 
 
 def pin(arr):

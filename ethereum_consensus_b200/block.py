@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from . import crypto
+from . import crypto, signing
 
 SITES = ("block_signature", "randao", "proposer_slashing", "attester_slashing", "attestation", "deposit", "voluntary_exit",
          "bls_to_execution_change", "sync_aggregate")
@@ -37,6 +37,7 @@ class _Entry:
     signature: bytes
     tolerant: bool = False
     eth_variant: bool = False  # eth_fast_aggregate_verify semantics (sync aggregate)
+    indices: Optional[List[int]] = None  # validator indices of the signers when they come from state.validators
 
 
 @dataclass
@@ -74,18 +75,59 @@ class SignatureSet:
             if i >= n:
                 raise InvalidIndexedAttestation(f"InvalidIndex({i})")
         self.add(site, [validator_pubkeys[i] for i in idx], signing_root, signature)
+        self.entries[-1].indices = idx
+
+    def add_by_index(self, site: str, validator_pubkeys, indices: Sequence[int], signing_root: bytes, signature: bytes) -> None:
+        """A check whose signer(s) are named by validator index (proposer, randao, slashings, exits): Appendix C rows
+        1-3, 7 draw their keys from `state.validators`, so registry mode applies to them."""
+        idx = [int(i) for i in indices]
+        self.add(site, [validator_pubkeys[i] for i in idx], signing_root, signature)
+        self.entries[-1].indices = idx
+
+    def add_sync_aggregate(self, committee_pubkeys: Sequence[bytes], sync_committee_bits: Sequence[bool], signature: bytes,
+                           state_slot: int, block_root_at_previous_slot: bytes, fork: "signing.Fork", genesis_validators_root: bytes,
+                           slots_per_epoch: int = 32, committee_indices: Optional[Sequence[int]] = None) -> None:
+        """`process_sync_aggregate` up to the BLS call (altair/block_processing.rs:216-243): participants = committee keys
+        whose bit is set (duplicates stay: a validator may sit in the committee more than once), message = signing root
+        of the block root at `max(slot, 1) - 1` under DOMAIN_SYNC_COMMITTEE at THAT slot's epoch (which `get_domain`
+        resolves to the previous fork version right after a fork), checked with `eth_fast_aggregate_verify`."""
+        if len(sync_committee_bits) != len(committee_pubkeys):
+            raise ValueError("sync_committee_bits and the committee differ in length")
+        previous_slot = max(int(state_slot), 1) - 1
+        domain = signing.get_domain(fork, genesis_validators_root, signing.DomainType.SyncCommittee,
+                                    signing.compute_epoch_at_slot(previous_slot, slots_per_epoch))
+        root = signing.compute_signing_root(block_root_at_previous_slot, domain)
+        sel = [j for j, b in enumerate(sync_committee_bits) if b]
+        self.add("sync_aggregate", [committee_pubkeys[j] for j in sel], root, signature, eth_variant=True)
+        if committee_indices is not None:
+            self.entries[-1].indices = [int(committee_indices[j]) for j in sel]
 
     # ---- one batch call for the whole block
-    def verify(self) -> np.ndarray:
-        """int32 code per entry, exactly what the per-call reference functions would have returned."""
+    def verify(self, registry: Optional["crypto.Registry"] = None) -> np.ndarray:
+        """int32 code per entry, exactly what the per-call reference functions would have returned.
+        With a `registry` (validated `state.validators` keys resident in HBM) the entries that name their signers by
+        validator index go through `…_batch_indexed`; entries whose key comes from the message itself (deposits,
+        bls-to-execution changes) always take the strict path.  Same codes either way."""
         t = len(self.entries)
         if t == 0:
             return np.zeros(0, dtype=np.int32)
-        pks = np.frombuffer(b"".join(p for e in self.entries for p in e.pubkeys) or b"", dtype=np.uint8)
-        off = np.cumsum([0] + [len(e.pubkeys) for e in self.entries]).astype(np.uint32)
-        msgs = np.frombuffer(b"".join(e.signing_root for e in self.entries), dtype=np.uint8)
-        sigs = np.frombuffer(b"".join(e.signature for e in self.entries), dtype=np.uint8)
-        codes = crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs).copy()
+        codes = np.zeros(t, dtype=np.int32)
+        by_index = [i for i, e in enumerate(self.entries) if registry is not None and e.indices is not None]
+        strict = [i for i in range(t) if i not in set(by_index)]
+        if strict:
+            ent = [self.entries[i] for i in strict]
+            pks = np.frombuffer(b"".join(p for e in ent for p in e.pubkeys) or b"", dtype=np.uint8)
+            off = np.cumsum([0] + [len(e.pubkeys) for e in ent]).astype(np.uint32)
+            msgs = np.frombuffer(b"".join(e.signing_root for e in ent), dtype=np.uint8)
+            sigs = np.frombuffer(b"".join(e.signature for e in ent), dtype=np.uint8)
+            codes[strict] = crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs)
+        if by_index:
+            ent = [self.entries[i] for i in by_index]
+            idx = np.array([j for e in ent for j in e.indices], dtype=np.uint32)
+            off = np.cumsum([0] + [len(e.indices) for e in ent]).astype(np.uint32)
+            msgs = np.frombuffer(b"".join(e.signing_root for e in ent), dtype=np.uint8)
+            sigs = np.frombuffer(b"".join(e.signature for e in ent), dtype=np.uint8)
+            codes[by_index] = registry.verify_batch(idx, off, msgs, sigs)
         for i, e in enumerate(self.entries):  # eth_fast_aggregate_verify: no participants + infinity signature is Ok
             if e.eth_variant and not e.pubkeys and e.signature == crypto.INFINITY_COMPRESSED_SIGNATURE:
                 codes[i] = 0
