@@ -53,6 +53,7 @@ def load_oracles():
     bls.orc_pk_sequence.argtypes = [C.c_char_p, C.c_char_p, sz, vp]
     bls.orc_fast_aggregate_verify.argtypes = [vp, sz, vp, sz, vp]
     bls.orc_fp_mul_count.restype = C.c_uint64
+    bls.orc_fp_sqr_count.restype = C.c_uint64
     bls.orc_key_validate.argtypes = [vp]
     ssz.orc_htr_beacon_state_deneb.argtypes = [vp, sz, ci, ci, vp]
     ssz.orc_htr_beacon_state_deneb.restype = ci
@@ -384,9 +385,12 @@ def main():
         orc_bls.orc_fast_aggregate_verify(w["pks"].ctypes.data, K, w["msgs"].ctypes.data, 32, w["sigs"].ctypes.data)
         cpu_1t = time.perf_counter() - t0
         fp_mul_per_tuple = int(orc_bls.orc_fp_mul_count())
+        fp_sqr_per_tuple = int(orc_bls.orc_fp_sqr_count())
         orc_bls.orc_fp_mul_count_reset()
         orc_bls.orc_key_validate(w["pks"].ctypes.data)
         fp_mul_per_key = int(orc_bls.orc_fp_mul_count())   # one key_validate: what the dominant kernel does per thread
+        fp_sqr_per_key = int(orc_bls.orc_fp_sqr_count())   # ... of which squarings (222 wide MADs each instead of 288)
+        mads_per_key = (fp_mul_per_key - fp_sqr_per_key) * 288 + fp_sqr_per_key * 222
 
         # integer-pipe denominators: IMAD.WIDE.U32 issues at one warp instruction per 4 cycles per SM
         # sub-partition = 32 lane-MADs / clk / SM (B300_MICROARCH "rt_SMSP"); the microbenchmarks are the measured
@@ -405,7 +409,7 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         dom = sum(dom_ms) / len(dom_ms)
         alg_bytes = T * (48 * K + 128)
-        k1_mads = T * K * fp_mul_per_key * 288 / (dom / 1e3) / 1e9   # algorithmic G MAD/s of the dominant kernel, per launch
+        k1_mads = T * K * mads_per_key / (dom / 1e3) / 1e9   # algorithmic G MAD/s of the dominant kernel, per launch
         imad_peak = max(imad_issue_peak, max(imad_meas.values()))
         ncu_traffic = None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture of THIS build
@@ -419,12 +423,13 @@ def main():
             # the LIMITING roofline of this path is the FMA-heavy integer pipe, not HBM: per launch of the
             # dominant kernel, algorithmic 32x32->64 multiply-adds (CPU oracle's instrumented product count for one
             # key_validate x 288) / that kernel's CUDA-event duration, against the IMAD.WIDE issue rate
-            "roofline": {"bound": "imad", "kernel": "k_g1_validate_r168", "achieved": k1_mads, "peak": imad_peak,
+            "roofline": {"bound": "imad", "kernel": {"7": "k_g1_validate_r168", "0": "k_g1_validate_main", "9": "k_g1_validate_main", "8": "k_g1_validate_r200", "10": "k_g1_validate_r184"}.get(os.environ.get("B200_G1_VARIANT", "0"), "k_g1_validate"), "achieved": k1_mads, "peak": imad_peak,
                          "unit": "G multiply-adds/s", "frac": k1_mads / imad_peak,
                          "peak_source": "IMAD.WIDE.U32 issue rate: 32 lane-MADs/clk/SM x SMs x SM clock sampled during the run "
                                         "(the larger of that and the on-device microbenchmarks)",
                          "peak_measured_microbench": imad_meas, "peak_issue_rate_model": imad_issue_peak,
-                         "fp_products_per_key": fp_mul_per_key, "mads_per_product": 288,
+                         "fp_products_per_key": fp_mul_per_key, "of_which_squarings": fp_sqr_per_key,
+                         "mads_per_product": 288, "mads_per_squaring": 222, "mads_per_key": mads_per_key,
                          "traffic": ncu_traffic, "algorithmic_bytes": T * K * (48 + 104),
                          "kernel_ms": dom, "share_of_step": dom / ms_dev},
             "hbm_roofline": {"bound": "hbm", "achieved": alg_bytes / (dom / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -432,9 +437,10 @@ def main():
                              "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                              "note": "not the binding limit: 48 B in + 104 B out per key against ~440 k multiply-adds"},
             "int_roofline": {"unit": "G 32x32 multiply-adds/s", "fp_mul_per_tuple_cpu_oracle_count": fp_mul_per_tuple,
-                             "achieved": value * fp_mul_per_tuple * 288 / 1e9 / world, "peak": imad_peak,
-                             "frac": value * fp_mul_per_tuple * 288 / 1e9 / world / imad_peak,
-                             "note": "whole step (all kernels + copies): algorithmic Fp products per tuple x 288 / device time per step",
+                             "squarings_per_tuple": fp_sqr_per_tuple,
+                             "achieved": value * ((fp_mul_per_tuple - fp_sqr_per_tuple) * 288 + fp_sqr_per_tuple * 222) / 1e9 / world, "peak": imad_peak,
+                             "frac": value * ((fp_mul_per_tuple - fp_sqr_per_tuple) * 288 + fp_sqr_per_tuple * 222) / 1e9 / world / imad_peak,
+                             "note": "whole step (all kernels + copies): algorithmic Fp products per tuple (288 MADs, squarings 222) / device time per step",
                              "alu_lop3_shf_iadd3_peak_gops": alu_peak},
             "cpu_baseline": {"value": sample / cpu_dt, "unit": "tuples/s", "cores": host_threads, "kind": "port",
                              "sample": f"first {sample} of the {T} tuples, {host_threads} host threads (affinity/cgroup-limited; machine has "

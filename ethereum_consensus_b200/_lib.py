@@ -56,6 +56,9 @@ _PROTOS = {
     "b200_state_root_incremental": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "b200_htr_beacon_state_deneb_shard": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b200_htr_beacon_state_deneb_combine": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200_compute_shuffled_indices": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "b200_get_active_validator_indices": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "b200_state_shuffled_active_indices": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_size_t)]),
     # multi-GPU (comm.cu): the exchange step lives inside the library
     "b200_comm_unique_id": (C.c_int32, [C.c_void_p]),
     "b200_comm_init": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),

@@ -8,6 +8,15 @@ execution order so the observable behaviour is the reference's:
 * `is_valid_indexed_attestation`'s host-side checks (non-empty, sorted, unique, index in range) run before any
   signature work and fail first (/root/reference/ethereum-consensus/src/phase0/helpers.rs:94-131).
 
+Deposits are NOT deferred with the rest: `apply_deposit` returns before `add_validator_to_registry` when
+the signature check fails (phase0/block_processing.rs:375-401), so the verdict decides a state mutation that later
+operations of the same block — and the state root — depend on.  Their signing root is state-independent
+(DOMAIN_DEPOSIT, genesis fork version, zero genesis_validators_root, key taken from the message), so
+`verify_deposits()` batches the block's deposit checks BEFORE `process_operations` and hands each verdict to
+`apply_deposit`; only the checks whose failure aborts the block are deferred to the end-of-block batch.  (A
+`SignatureSet` still accepts `tolerant` entries — the parity tests exercise the whole Appendix C set in one batch —
+and reports them through `skipped_deposits`.)
+
 Sites, in the order of deneb `process_block` (deneb/block_processing.rs:402-408, spec/mod.rs:219-230):
 block proposer, randao, proposer slashings, attester slashings, attestations, deposits, voluntary exits,
 bls-to-execution changes, sync aggregate.
@@ -23,6 +32,30 @@ from . import crypto, signing
 
 SITES = ("block_signature", "randao", "proposer_slashing", "attester_slashing", "attestation", "deposit", "voluntary_exit",
          "bls_to_execution_change", "sync_aggregate")
+
+
+def deposit_signing_root(pubkey: bytes, withdrawal_credentials: bytes, amount: int, genesis_fork_version: bytes = b"\x00" * 4) -> bytes:
+    """Signing root of `DepositMessage{pubkey, withdrawal_credentials, amount}` (phase0/operations.rs:74-80) under
+    `compute_domain(DEPOSIT, None, None)` = genesis fork version + zero root (phase0/block_processing.rs:387)."""
+    from . import ssz
+    pk_root = ssz.merkleize(bytes(pubkey) + bytes(16), 2)                       # ByteVector<48>: two chunks
+    leaves = pk_root + bytes(withdrawal_credentials) + int(amount).to_bytes(8, "little").ljust(32, b"\x00")
+    obj = ssz.merkleize(leaves, 4)                                              # 3 fields padded to 4 leaves
+    return signing.compute_signing_root(obj, signing.compute_domain(signing.DomainType.Deposit, genesis_fork_version, bytes(32)))
+
+
+def verify_deposits(deposits: Sequence[tuple], genesis_fork_version: bytes = b"\x00" * 4) -> List[bool]:
+    """The block's deposit signature checks as ONE batch, before `process_operations`: `deposits` = the
+    (pubkey, withdrawal_credentials, amount, signature) of every deposit whose key is not in the registry yet.
+    verdict[i] is what `verify_signed_data(...).is_ok()` returns inside `apply_deposit`
+    (phase0/block_processing.rs:387-392): False means "skip this deposit, no state change", never a block failure."""
+    if not deposits:
+        return []
+    pks = np.frombuffer(b"".join(bytes(crypto.PublicKey(d[0])) for d in deposits), dtype=np.uint8)
+    off = np.arange(len(deposits) + 1, dtype=np.uint32)
+    msgs = np.frombuffer(b"".join(deposit_signing_root(d[0], d[1], d[2], genesis_fork_version) for d in deposits), dtype=np.uint8)
+    sigs = np.frombuffer(b"".join(bytes(crypto.Signature(d[3])) for d in deposits), dtype=np.uint8)
+    return [int(c) == 0 for c in crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs)]
 
 
 class InvalidIndexedAttestation(ValueError):

@@ -8,6 +8,7 @@
 #include "comm.h"
 #include "engine.h"
 #include "sha256.cuh"
+#include "shuffle.h"
 #include "ssz_plan.h"
 
 namespace b200 {
@@ -469,6 +470,38 @@ int32_t b200_htr_beacon_state_deneb_combine(const uint8_t* ssz, size_t len, int3
     rc = build_beacon_state_combine_plan(p, ssz, len, preset, world, all_roots, outs);
     if (rc) return rc;
     return run_oneshot(e, p, outs, out);
+}
+
+// get_active_validator_indices + compute_shuffled_indices on a device-resident state: the registry never leaves HBM;
+// only the shuffled index list (8 B per active validator) comes back.
+int32_t b200_state_shuffled_active_indices(b200_state* h, uint64_t epoch, const uint8_t seed[32], uint32_t rounds, uint64_t* out,
+                                           size_t* out_n) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!h || !h->uploaded || !seed || !out_n) return B200_ERR_BAD_ARG;
+    *out_n = 0;
+    const uint64_t n = big_count(h, 0);
+    if (n == 0) return B200_SUCCESS;
+    if (!out) return B200_ERR_BAD_ARG;
+    uint64_t field_off = 0; size_t nbytes = 0;
+    if (!h->plan.chain_field(0, &field_off, &nbytes)) return B200_ERR_BAD_ARG;
+    uint64_t *d_act, *d_out;
+    rc = shuffle_scratch(e, n, &d_act, &d_out);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaEventRecord(e.ev0, e.stream));
+    uint64_t cnt = 0;
+    rc = active_indices_on_device(e, static_cast<const uint8_t*>(h->fields.p) + field_off, n, epoch, d_act, &cnt);
+    if (rc) return rc;
+    rc = shuffle_on_device(e, d_act, cnt, seed, rounds, d_out);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaEventRecord(e.ev1, e.stream));
+    if (cnt) B200_CUDA_TRY(cudaMemcpyAsync(out, d_out, cnt * 8, cudaMemcpyDeviceToHost, e.stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, e.ev0, e.ev1));
+    *out_n = size_t(cnt);
+    return B200_SUCCESS;
 }
 
 // One call, all ranks: slices + small fields -> ncclAllGather of 5 x 32 B on the engine stream -> finisher.

@@ -99,12 +99,23 @@ def hash_tree_root_beacon_state(ssz, preset: str = "mainnet") -> bytes:
     return bytes(out)
 
 
+def _count_validators(ssz, preset: str) -> int:
+    """Length of `validators` read from the two offsets in the fixed part (deneb/beacon_state.rs:26-63)."""
+    import struct
+    hist = 8192 if preset == "mainnet" else 64
+    o = 8 + 32 + 8 + 16 + 112 + 2 * 32 * hist + 4 + 72 + 4 + 8   # ... eth1_deposit_index, then the validators offset
+    head = bytes(np.frombuffer(ssz, dtype=np.uint8, count=o + 8)) if not isinstance(ssz, np.ndarray) else bytes(ssz.reshape(-1).view(np.uint8)[: o + 8])
+    v_off, b_off = struct.unpack_from("<II", head, o)
+    return (b_off - v_off) // 121
+
+
 class DeviceBeaconState:
     """A deneb BeaconState resident in HBM: upload once, `hash_tree_root()` costs kernels only."""
 
     def __init__(self, ssz, preset: str = "mainnet"):
         nbytes = ssz.nbytes if hasattr(ssz, "nbytes") else len(ssz)
         self._h = C.c_void_p()
+        self.n_validators = _count_validators(ssz, preset)
         _rc(_lib.lib().b200_state_upload_deneb(_lib.ptr(ssz), nbytes, _lib.PRESET[preset], C.byref(self._h)),
             "state_upload")
 

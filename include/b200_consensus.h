@@ -122,6 +122,22 @@ B200_API int32_t b200_htr_beacon_state_deneb_shard(const uint8_t* ssz, size_t le
 B200_API int32_t b200_htr_beacon_state_deneb_combine(const uint8_t* ssz, size_t len, int32_t preset, int32_t world,
                                             const uint8_t* all_roots /* world*5*32 */, uint8_t out[32]);
 
+/* ---- committee shuffling: the step before the BLS hot path ---------------------------------- */
+/* compute_shuffled_indices — /root/reference/ethereum-consensus/src/phase0/helpers.rs:287-360 (whole list; equal to
+ * mapping every position through compute_shuffled_index, :249-283): out[i] = indices[shuffled_index(i, n, seed)].
+ * `indices` == NULL means the identity list 0..n-1; `rounds` = SHUFFLE_ROUND_COUNT (90 on mainnet, 10 on minimal). */
+B200_API int32_t b200_compute_shuffled_indices(const uint64_t* indices, size_t n, const uint8_t seed[32], uint32_t rounds,
+                                               uint64_t* out);
+/* get_active_validator_indices — phase0/helpers.rs:646-676 over n x 121 bytes of SSZ Validator records
+ * (activation_epoch <= epoch < exit_epoch); `out` must hold n entries, *out_n receives the count. */
+B200_API int32_t b200_get_active_validator_indices(const uint8_t* validators_ssz, size_t n, uint64_t epoch, uint64_t* out,
+                                                   size_t* out_n);
+/* Both steps on a device-resident state (b200_state_upload_deneb): the registry never leaves HBM, only the shuffled
+ * active-index list returns.  get_beacon_committee (phase0/helpers.rs:775-806) is then the slice
+ * [len*index/count, len*(index+1)/count) of `out` (compute_committee, :459-483). */
+B200_API int32_t b200_state_shuffled_active_indices(b200_state* handle, uint64_t epoch, const uint8_t seed[32], uint32_t rounds,
+                                                    uint64_t* out, size_t* out_n);
+
 /* ---- multi-GPU: one process per GPU, the exchange step lives INSIDE the library (SURVEY.md §8b `b200_init(n_gpus)`,
  * §8e).  The reference is single-process (no counterpart); a Rust host with one process per GPU calls:
  *   rank 0:   b200_comm_unique_id(id)  -> ships the 128 bytes to the other ranks by any means it likes (pipe, file, TCP)

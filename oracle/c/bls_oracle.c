@@ -38,10 +38,11 @@ static const fp P = {{0xb9feffffffffaaabull, 0x1eabfffeb153ffffull, 0x6730d2a0f6
 static const uint64_t N0 = 0x89f3fffcfffcfffdull; /* -p^-1 mod 2^64 */
 static fp R1, R2;                                  /* 2^384 mod p, 2^768 mod p (computed at init) */
 /* instrumented Fp-product counter: enabled only between reset() and count(), single-threaded use */
-static uint64_t g_fp_mul_count;
+static uint64_t g_fp_mul_count, g_fp_sqr_count;
 static int g_count_on;
 ORC_EXPORT uint64_t orc_fp_mul_count(void) { g_count_on = 0; return g_fp_mul_count; }
-ORC_EXPORT void orc_fp_mul_count_reset(void) { g_fp_mul_count = 0; g_count_on = 1; }
+ORC_EXPORT uint64_t orc_fp_sqr_count(void) { return g_fp_sqr_count; }   /* how many of those products were squarings */
+ORC_EXPORT void orc_fp_mul_count_reset(void) { g_fp_mul_count = 0; g_fp_sqr_count = 0; g_count_on = 1; }
 
 static int fp_is_zero(const fp *a) { uint64_t x = 0; for (int i = 0; i < 6; i++) x |= a->l[i]; return x == 0; }
 static int fp_eq(const fp *a, const fp *b) { uint64_t x = 0; for (int i = 0; i < 6; i++) x |= a->l[i] ^ b->l[i]; return x == 0; }
@@ -80,7 +81,7 @@ static void fp_mul(fp *r, const fp *a, const fp *b) {
  * once, doubled, plus the 6 squares, then a separate 6-round Montgomery reduction.  Counted as one product. */
 static void fp_sqr(fp *r, const fp *a) {
     uint64_t t[13] = {0};
-    if (g_count_on) g_fp_mul_count++;
+    if (g_count_on) { g_fp_mul_count++; g_fp_sqr_count++; }
     for (int i = 0; i < 5; i++) {                      /* off-diagonal a_i a_j, i < j */
         u128 c = 0;
         for (int j = i + 1; j < 6; j++) { c += (u128)a->l[i] * a->l[j] + t[i + j]; t[i + j] = (uint64_t)c; c >>= 64; }
