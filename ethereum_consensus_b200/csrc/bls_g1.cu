@@ -50,16 +50,9 @@ __global__ void __maxnreg__(168) k_g1_validate_r168(const uint8_t* __restrict__ 
                                                     int32_t* __restrict__ codes) {
     g1_validate_body(keys, n, out, codes);
 }
-// 10 warps per SM: 320 x 200 registers = 64 000 (register allocation is per warp in units of 8 per thread)
-__global__ void __maxnreg__(200) k_g1_validate_r200(const uint8_t* __restrict__ keys, uint32_t n, G1Aff* __restrict__ out,
-                                                    int32_t* __restrict__ codes) {
-    g1_validate_body(keys, n, out, codes);
-}
-// 11 warps per SM: 352 x 184 registers (72 B of spills at ptxas -O1)
-__global__ void __maxnreg__(184) k_g1_validate_r184(const uint8_t* __restrict__ keys, uint32_t n, G1Aff* __restrict__ out,
-                                                    int32_t* __restrict__ codes) {
-    g1_validate_body(keys, n, out, codes);
-}
+// (Occupancies between 8 and 12 warps per SM do not exist for this kernel: the register file is handed out in units of
+// four warps, so 9-, 10- and 11-warp CTAs at 224 / 200 / 184 registers all fail to launch — measured, "too many
+// resources requested" — and the choice is 8 warps at <= 256 registers or 12 warps at <= 168.)
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
                                                                 G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
@@ -205,7 +198,7 @@ static size_t with_pow_tab(K kernel, unsigned threads) {
 // tuning knob (B200_G1_VARIANT): 0: 256 threads, 224 registers (default); 7: 384 threads, 168 registers;
 // threads x min CTAs/SM = 1: 128x2, 2: 128x3, 3: 256x2, 4: 128x4, 5: 256x1 uncapped
 static int g_g1_variant = 0;
-void set_g1_variant(int v) { if (v >= 0 && v <= 10) g_g1_variant = v; }
+void set_g1_variant(int v) { if (v >= 0 && v <= 7) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -216,9 +209,6 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
     case 4: k_g1_validate<128, 4><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 4>, 128), st>>>(keys, n, out, codes); break;
     case 5: k_g1_validate<256, 1><<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate<256, 1>, 256), st>>>(keys, n, out, codes); break;
     case 0: k_g1_validate_main<<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate_main, 256), st>>>(keys, n, out, codes); break;
-    case 8: k_g1_validate_r200<<<(n + 319) / 320, 320, with_pow_tab(k_g1_validate_r200, 320), st>>>(keys, n, out, codes); break;   // 10 warps / SM
-    case 10: k_g1_validate_r184<<<(n + 351) / 352, 352, with_pow_tab(k_g1_validate_r184, 352), st>>>(keys, n, out, codes); break;  // 11 warps / SM
-    case 9: k_g1_validate_main<<<(n + 287) / 288, 288, with_pow_tab(k_g1_validate_main, 288), st>>>(keys, n, out, codes); break;  // 9 warps / SM
     default: k_g1_validate_r168<<<(n + 383) / 384, 384, with_pow_tab(k_g1_validate_r168, 384), st>>>(keys, n, out, codes); break;
     }
 }

@@ -5,6 +5,7 @@
 //   POINT_NOT_ON_CURVE(2), POINT_NOT_IN_GROUP(3), PK_IS_INFINITY(6)
 #pragma once
 #include "curve.cuh"
+#include "fpl.cuh"
 
 namespace b200 {
 
@@ -68,12 +69,57 @@ B200_HD bool g1_in_subgroup(const G1Aff& p) {
     return jac_eq_aff(t2, bx, ny);
 }
 
-// blst `PublicKey::key_validate`
+// ---- the same two steps on lazily reduced field elements (fpl.cuh): what the per-key kernel runs ----------------
+// decompression: identical checks and codes as g1_uncompress; y = (x^3 + 4)^((p+1)/4) with no reduction inside the chain
+B200_HD int32_t g1_uncompress_lazy(G1Aff& out, const uint8_t b[48]) {
+    const uint8_t f = b[0];
+    out.inf = 0;
+    if (!(f & 0x80)) return BLS_BAD_ENCODING;
+    if (f & 0x40) {
+        if ((f & 0x3f) == 0 && bytes_all_zero(b + 1, 47)) { out.inf = 1; out.x = fp_zero(); out.y = fp_zero(); return BLS_SUCCESS; }
+        return BLS_BAD_ENCODING;
+    }
+    Fp x;
+    if (!fp_from_be48_masked(x, b, true)) return BLS_BAD_ENCODING;
+    FpL xl = fpl_from_fp(x), y2, yl, c;
+    f_sqr(y2, xl);
+    f_mul(y2, y2, xl);
+    f_add(y2, y2, curve_b<FpL>());
+    fpl_pow(yl, y2, B200_EXP_TABLE(exp_sqrt));
+    f_sqr(c, yl);
+    if (!f_eq(c, y2)) return BLS_POINT_NOT_ON_CURVE;
+    Fp y = fpl_canon(yl);
+    if (fp_is_lex_largest(y) != ((f & 0x20) != 0)) fp_neg(y, y);
+    out.x = x; out.y = y;
+    return BLS_SUCCESS;
+}
+// phi(P) == -[z^2]P on FpL (the templated Jacobian formulas of curve.cuh, every intermediate in [0, 2p))
+B200_HD bool g1_in_subgroup_lazy(const G1Aff& p) {
+    if (p.inf) return true;
+    const FpL px = fpl_from_fp(p.x), py = fpl_from_fp(p.y);
+    Jac<FpL> t, t2;
+    jac_mul_u64(t, px, py, B200_Z_ABS);
+    jac_mul_u64_jac(t2, t, B200_Z_ABS);
+    const Fp beta = B200_FP_BETA;
+    FpL bx, ny;
+    f_mul(bx, px, fpl_from_fp(beta));
+    f_neg(ny, py);
+    return jac_eq_aff(t2, bx, ny);
+}
+
+// blst `PublicKey::key_validate`.  -DB200_G1_CANONICAL_FP selects the fully reduced arithmetic (round 1's path).
 B200_HD int32_t g1_key_validate(G1Aff& out, const uint8_t b[48]) {
+#if defined(B200_G1_CANONICAL_FP)
     int32_t rc = g1_uncompress(out, b);
     if (rc) return rc;
     if (out.inf) return BLS_PK_IS_INFINITY;
     if (!g1_in_subgroup(out)) return BLS_POINT_NOT_IN_GROUP;
+#else
+    int32_t rc = g1_uncompress_lazy(out, b);
+    if (rc) return rc;
+    if (out.inf) return BLS_PK_IS_INFINITY;
+    if (!g1_in_subgroup_lazy(out)) return BLS_POINT_NOT_IN_GROUP;
+#endif
     return BLS_SUCCESS;
 }
 

@@ -22,6 +22,8 @@ from oracle import bls_oracle as bo  # noqa: E402  (generator-time checks only)
 P = bo.P
 Z_ABS = bo.Z_ABS
 
+MIX_LIGHT = False  # True: ready light ops ride in the idle lanes of heavy rounds (measured offline: halves the rounds but doubles the rounds that pay for a product - a loss)
+
 # opcodes (must match pairing_vm.cuh)
 NOP, MUL, SQR, MULFP, INV, ADD, SUB, NEG, DBL, CONJ, MULXI, COPY, LDC = range(13)
 HEAVY = {MUL: "mul", SQR: "sqr", MULFP: "mulfp", INV: "inv"}
@@ -350,12 +352,21 @@ def schedule(tr, outputs, team, window=None):
             op = ins[i][0]
             cl = HEAVY.get(op, "light")
             classes.setdefault(cl, []).append(i)
-        # light ops are nearly free: flush them first so heavy rounds see the widest ready set
-        if "light" in classes:
-            cl = "light"
+        heavy_classes = [c for c in classes if c != "light"]
+        if MIX_LIGHT and heavy_classes:
+            # a heavy round whenever one is possible; lanes the heavy class leaves idle carry ready light ops (they
+            # diverge from the product code, but a light op is ~4 % of a product and would otherwise cost a round)
+            cl = max(heavy_classes, key=lambda c: max(prio[i] for i in classes[c]))
+            pick = sorted(classes[cl], key=lambda i: -prio[i])[:team]
+            if len(pick) < team and "light" in classes:
+                pick += sorted(classes["light"], key=lambda i: -prio[i])[:team - len(pick)]
         else:
-            cl = max(classes, key=lambda c: max(prio[i] for i in classes[c]))
-        pick = sorted(classes[cl], key=lambda i: -prio[i])[:team]
+            # light ops are nearly free: flush them first so heavy rounds see the widest ready set
+            if "light" in classes:
+                cl = "light"
+            else:
+                cl = max(classes, key=lambda c: max(prio[i] for i in classes[c]))
+            pick = sorted(classes[cl], key=lambda i: -prio[i])[:team]
         r = len(rounds)
         rounds.append(pick)
         for i in pick:
@@ -494,7 +505,7 @@ def emit(team, miller, final):
         words = []
         heavy = 0
         for row in rounds:
-            if row and row[0][0] in HEAVY:
+            if row and any(o[0] in HEAVY for o in row):
                 heavy += 1
             for k in range(team):
                 if k < len(row):
@@ -532,7 +543,7 @@ def main():
     window_final = int(sys.argv[3]) if len(sys.argv) > 3 else (48 if team == 16 else 96)
     miller, final = build(team, window, window_final)
     for name, (rounds, nslots, _o) in (("miller", miller), ("final", final)):
-        heavy = [r for r in rounds if r and r[0][0] in HEAVY]
+        heavy = [r for r in rounds if r and any(o[0] in HEAVY for o in r)]
         util = sum(len(r) for r in heavy) / max(1, len(heavy) * team)
         print(f"{name}: {len(rounds)} rounds ({len(heavy)} heavy, lane utilisation {util:.2f}), {nslots} slots, "
               f"{sum(len(r) for r in rounds)} instructions")
