@@ -423,7 +423,7 @@ def main():
             # the LIMITING roofline of this path is the FMA-heavy integer pipe, not HBM: per launch of the
             # dominant kernel, algorithmic 32x32->64 multiply-adds (CPU oracle's instrumented product count for one
             # key_validate x 288) / that kernel's CUDA-event duration, against the IMAD.WIDE issue rate
-            "roofline": {"bound": "imad", "kernel": {"7": "k_g1_validate_r168", "0": "k_g1_validate_main"}.get(os.environ.get("B200_G1_VARIANT", "0"), "k_g1_validate"), "achieved": k1_mads, "peak": imad_peak,
+            "roofline": {"bound": "imad", "kernel": {"7": "k_g1_validate_r168", "0": "k_g1_validate_main", "6": "k_g1_validate_r128"}.get(os.environ.get("B200_G1_VARIANT", "7"), "k_g1_validate"), "achieved": k1_mads, "peak": imad_peak,
                          "unit": "G multiply-adds/s", "frac": k1_mads / imad_peak,
                          "peak_source": "IMAD.WIDE.U32 issue rate: 32 lane-MADs/clk/SM x SMs x SM clock sampled during the run "
                                         "(the larger of that and the on-device microbenchmarks)",

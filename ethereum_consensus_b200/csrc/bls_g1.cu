@@ -12,7 +12,12 @@
 #if defined(B200_G1_SQR_VIA_MUL)
 #define B200_FP_SQR_VIA_MUL 1
 #endif
-#if defined(B200_G1_CALL_MUL)  // A/B knob: by-value function calls instead of inlined products in the per-key kernel
+// Products as by-value function CALLS (operands and result in registers, 0-byte frames) instead of ~70 inlined copies:
+// the inlined kernel is 0.5 MB of straight-line code, far beyond the instruction caches, and only pays at 8 warps per SM
+// where the warps stay in step.  With calls the kernel body is 170 KB and 12 warps per SM win.  Measured on B200
+// (profiles/r2_ab_variants.txt, 2^21 keys, lazily reduced arithmetic): inline 8 warps 118.6 ms, inline 12 warps 125.6,
+// calls 8 warps 124.7, **calls 12 warps 111.8**.  -DB200_G1_INLINE_MUL restores the inlined products.
+#if !defined(B200_G1_INLINE_MUL)
 #define B200_FP_MUL_CALL 1
 #endif
 // fp_pow's window table in dynamic shared memory (fp.cuh): every kernel here that can reach fp_pow is launched through
@@ -38,8 +43,9 @@ __device__ __forceinline__ void g1_validate_body(const uint8_t* __restrict__ key
     codes[i] = rc;
     if (rc == BLS_SUCCESS) out[i] = p;
 }
-// Default (variant 0): 256-thread CTAs at 224 registers (8 warps per SM, no spills).  Variant 7: 384 threads capped at
-// 168 registers = 12 warps per SM.  Measured on B200, 2^21 keys: at ptxas' default level 164.5 vs 161.9 ms (round 1,
+// Default (variant 7): 384 threads capped at 168 registers = 12 warps per SM (with call-based products, see the top of
+// this file).  Variant 0: 256-thread CTAs at 224 registers (8 warps per SM, no spills).  Variant 6: 512 threads at 128
+// registers = 16 warps per SM.  Measured on B200, 2^21 keys: at ptxas' default level 164.5 vs 161.9 ms (round 1,
 // variant 7 was the default); at -O1 the spill-free variant wins, 132.1 vs 136.0 ms, and 128.2 vs 143.2 ms with the
 // dedicated square (profiles/r2_ab_variants.txt).  (__maxnreg__ cannot be combined with __launch_bounds__.)
 __global__ void __maxnreg__(224) k_g1_validate_main(const uint8_t* __restrict__ keys, uint32_t n, G1Aff* __restrict__ out,
@@ -53,6 +59,10 @@ __global__ void __maxnreg__(168) k_g1_validate_r168(const uint8_t* __restrict__ 
 // (Occupancies between 8 and 12 warps per SM do not exist for this kernel: the register file is handed out in units of
 // four warps, so 9-, 10- and 11-warp CTAs at 224 / 200 / 184 registers all fail to launch — measured, "too many
 // resources requested" — and the choice is 8 warps at <= 256 registers or 12 warps at <= 168.)
+__global__ void __maxnreg__(128) k_g1_validate_r128(const uint8_t* __restrict__ keys, uint32_t n, G1Aff* __restrict__ out,
+                                                    int32_t* __restrict__ codes) {
+    g1_validate_body(keys, n, out, codes);
+}
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
                                                                 G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
@@ -195,9 +205,9 @@ static size_t with_pow_tab(K kernel, unsigned threads) {
     if (n_seen < 16) { seen[n_seen] = key; granted[n_seen++] = bytes; }
     return bytes;
 }
-// tuning knob (B200_G1_VARIANT): 0: 256 threads, 224 registers (default); 7: 384 threads, 168 registers;
+// tuning knob (B200_G1_VARIANT): 7: 384 threads, 168 registers (default); 0: 256 threads, 224 registers; 6: 512 threads, 128 registers;
 // threads x min CTAs/SM = 1: 128x2, 2: 128x3, 3: 256x2, 4: 128x4, 5: 256x1 uncapped
-static int g_g1_variant = 0;
+static int g_g1_variant = 7;
 void set_g1_variant(int v) { if (v >= 0 && v <= 7) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;
@@ -208,6 +218,7 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
     case 3: k_g1_validate<256, 2><<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate<256, 2>, 256), st>>>(keys, n, out, codes); break;
     case 4: k_g1_validate<128, 4><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 4>, 128), st>>>(keys, n, out, codes); break;
     case 5: k_g1_validate<256, 1><<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate<256, 1>, 256), st>>>(keys, n, out, codes); break;
+    case 6: k_g1_validate_r128<<<(n + 511) / 512, 512, with_pow_tab(k_g1_validate_r128, 512), st>>>(keys, n, out, codes); break;
     case 0: k_g1_validate_main<<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate_main, 256), st>>>(keys, n, out, codes); break;
     default: k_g1_validate_r168<<<(n + 383) / 384, 384, with_pow_tab(k_g1_validate_r168, 384), st>>>(keys, n, out, codes); break;
     }

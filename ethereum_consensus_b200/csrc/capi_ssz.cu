@@ -77,7 +77,9 @@ struct b200_state {
     size_t len = 0;
     int preset = 0;
     StateOffsets so;
-    std::vector<uint32_t> dirty[5];  // per big list: changed first-job inputs (records / 32-byte chunks), unsorted
+    // per chain (5 big lists, then block_roots / state_roots / randao_mixes / slashings): changed first-job inputs
+    // (Validator records / 32-byte chunks), unsorted
+    std::vector<uint32_t> dirty[9];
     bool small_dirty = false;
     std::vector<std::pair<const uint8_t*, const uint8_t*>> small_ranges;  // patched shadow bytes since the last root
     bool pinned_head = false, pinned_tail = false;
@@ -403,13 +405,18 @@ int32_t b200_state_update_bytes(b200_state* h, uint64_t ssz_offset, const uint8_
         }
         h->small_dirty = true;
     }
-    // (2) the parts inside big lists: copy into the resident list, mark the covered inputs dirty
-    for (int f = 0; f < 5; f++) {
-        const uint64_t a = h->so.var[kBigVar[f]], b = h->so.var[kBigVar[f] + 1];
+    // (2) the parts inside big lists and inside the four big vectors (chains 5..8): copy into the resident field, mark the
+    //     covered inputs dirty
+    const uint64_t vec_lo[4] = {h->so.block_roots, h->so.state_roots, h->so.randao_mixes, h->so.slashings};
+    for (int f = 0; f < 9; f++) {
+        if (size_t(f) >= h->plan.n_chains()) break;
+        uint64_t field_off = 0; size_t nbytes = 0;
+        const bool staged = h->plan.chain_field(f, &field_off, &nbytes);
+        const uint64_t a = f < 5 ? h->so.var[kBigVar[f]] : vec_lo[f - 5];
+        const uint64_t b = f < 5 ? h->so.var[kBigVar[f] + 1] : a + nbytes;
         const uint64_t x = std::max(a, lo), y = std::min(b, hi);
         if (x >= y) continue;
-        uint64_t field_off = 0; size_t nbytes = 0;
-        if (!h->plan.chain_field(f, &field_off, &nbytes)) return B200_ERR_BAD_ARG;
+        if (!staged) return B200_ERR_BAD_ARG;
         B200_CUDA_TRY(e.staging.reserve(y - x));
         memcpy(e.staging.p, data + (x - lo), y - x);
         B200_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(h->fields.p) + field_off + (x - a), e.staging.p, y - x,
@@ -430,7 +437,7 @@ int32_t b200_state_root_incremental(b200_state* h, uint8_t out[32]) {
     rc = replan_if_small_dirty(e, h);
     if (rc) return rc;
     std::vector<std::vector<uint32_t>> dirty(h->plan.n_chains());
-    for (int f = 0; f < 5 && size_t(f) < dirty.size(); f++) {
+    for (int f = 0; f < 9 && size_t(f) < dirty.size(); f++) {
         dirty[size_t(f)] = h->dirty[f];
         std::sort(dirty[size_t(f)].begin(), dirty[size_t(f)].end());
         dirty[size_t(f)].erase(std::unique(dirty[size_t(f)].begin(), dirty[size_t(f)].end()), dirty[size_t(f)].end());

@@ -224,6 +224,25 @@ __global__ void __launch_bounds__(kStageThreads) k_merkle_reduce_sparse(const __
     }
     store_node(jb.dst + o * 8, out);
 }
+// REDUCE jobs of one tree level of several lists in one launch
+__global__ void __launch_bounds__(kStageThreads) k_merkle_reduce_sparse_multi(const __grid_constant__ SparseDesc sd) {
+    int j = 0;
+#pragma unroll 1
+    for (int k = 1; k < sd.njobs; k++)
+        if (blockIdx.x >= sd.block_begin[k]) j = k;
+    const Job& jb = sd.jobs[j];
+    const uint32_t t = (blockIdx.x - sd.block_begin[j]) * kStageThreads + threadIdx.x;
+    if (t >= sd.n_sel[j]) return;
+    const uint64_t o = sd.sel[sd.sel_begin[j] + t];
+    uint32_t out[8];
+    switch (jb.nlev) {
+    case 0: subtree<0>(jb, sd.zero_nodes, o, out); break;
+    case 1: subtree<1>(jb, sd.zero_nodes, o << 1, out); break;
+    case 2: subtree<2>(jb, sd.zero_nodes, o << 2, out); break;
+    default: subtree<3>(jb, sd.zero_nodes, o << 3, out); break;
+    }
+    store_node(jb.dst + o * 8, out);
+}
 // dst[idx[i] * elem .. +elem) = vals[i * elem .. +elem)   (elem in {1, 8, 121}: byte copies, any alignment)
 __global__ void k_scatter_elements(uint8_t* __restrict__ dst, const uint64_t* __restrict__ idx, const uint8_t* __restrict__ vals,
                                    uint32_t n, uint32_t elem) {
@@ -296,6 +315,10 @@ void launch_sparse(const Job& jb, const uint32_t* zero_nodes, const uint32_t* se
     const uint32_t nb = (n_sel + kStageThreads - 1) / kStageThreads;
     if (jb.type == JOB_VALIDATORS) k_validator_roots_sparse<<<nb, kStageThreads, 0, st>>>(jb, sel, n_sel);
     else k_merkle_reduce_sparse<<<nb, kStageThreads, 0, st>>>(jb, zero_nodes, sel, n_sel);
+}
+void launch_sparse_multi(const SparseDesc& sd, void* stream) {
+    if (sd.njobs == 0 || sd.block_begin[sd.njobs] == 0) return;
+    k_merkle_reduce_sparse_multi<<<sd.block_begin[sd.njobs], kStageThreads, 0, static_cast<cudaStream_t>(stream)>>>(sd);
 }
 void launch_scatter(uint8_t* dst, const uint64_t* idx, const uint8_t* vals, uint32_t n, uint32_t elem, void* stream) {
     if (!n) return;

@@ -34,6 +34,19 @@ struct StageDesc {
     const uint32_t* zero_nodes;  // device: zero-subtree hashes, word form, 65 x 8 words
 };
 
+// One dirty-path launch for the same tree level of several lists (incremental re-hash): job k recomputes outputs
+// sel[sel_begin[k] .. sel_begin[k] + n_sel[k]) — blocks [block_begin[k], block_begin[k+1]) belong to job k.
+constexpr int kMaxSparseJobs = 12;
+struct SparseDesc {
+    Job jobs[kMaxSparseJobs];
+    uint32_t sel_begin[kMaxSparseJobs];
+    uint32_t n_sel[kMaxSparseJobs];
+    uint32_t block_begin[kMaxSparseJobs + 1];
+    int njobs;
+    const uint32_t* zero_nodes;
+    const uint32_t* sel;
+};
+
 // finisher op: arena[dst] = H(arena[a] || arena[b]) (kind 0) or arena[dst] = arena[a] (kind 1: gathers nodes into the
 // contiguous send region of a multi-GPU exchange); indices are node indices into the arena
 struct FinOp {
@@ -49,6 +62,7 @@ void launch_validators(const Job& jb, void* stream);
 void launch_stage(const StageDesc& sd, void* stream);
 // dirty-path variants: thread t handles output sel[t] (JOB_VALIDATORS or JOB_REDUCE only)
 void launch_sparse(const Job& jb, const uint32_t* zero_nodes, const uint32_t* sel, uint32_t n_sel, void* stream);
+void launch_sparse_multi(const SparseDesc& sd, void* stream);
 void launch_scatter(uint8_t* dst, const uint64_t* idx, const uint8_t* vals, uint32_t n, uint32_t elem, void* stream);
 // waves [0, nwaves) of `wave_end` (cumulative op counts); the first wave starts at op `first_op`
 void launch_finisher(uint32_t* arena, const FinOp* ops, const uint32_t* wave_end, int nwaves, void* stream, uint32_t first_op = 0);

@@ -92,7 +92,13 @@ void SszPlan::add_job(size_t stage, const PJob& j) {
     if (stages_.size() <= stage) stages_.resize(stage + 1);
     stages_[stage].push_back(j);
     stages_[stage].back().chain = cur_chain_;
+    stages_[stage].back().copy = cur_copy_;
     if (cur_chain_ >= 0) chains_[size_t(cur_chain_)].jobs.emplace_back(int(stage), stages_[stage].size() - 1);
+}
+int SszPlan::copy_of(uint64_t field_off) const {
+    for (size_t i = 0; i < copies_.size(); i++)
+        if (copies_[i].field_off == field_off) return int(i);
+    return -1;
 }
 bool SszPlan::chain_field(int c, uint64_t* field_off, size_t* nbytes) const {
     if (c < 0 || size_t(c) >= chains_.size() || chains_[size_t(c)].copy < 0) return false;
@@ -127,12 +133,17 @@ uint32_t SszPlan::wide_nodes(PSrc src, bool raw, uint64_t n, int level, int dept
 }
 uint32_t SszPlan::wide_chunks(uint64_t field_off, uint64_t n_chunks, int depth_target) {
     PSrc s; s.in_arena = false; s.off = field_off;
-    return wide_nodes(s, true, n_chunks, 0, depth_target, 0);
+    cur_copy_ = copy_of(field_off);
+    const uint32_t r = wide_nodes(s, true, n_chunks, 0, depth_target, 0);
+    cur_copy_ = -1;
+    return r;
 }
 uint32_t SszPlan::wide_records(uint32_t type, uint64_t field_off, uint64_t n, int depth_target) {
     if (n == 0) return zero(depth_target);
+    cur_copy_ = copy_of(field_off);
     PJob j;
     j.type = type; j.src.in_arena = false; j.src.off = field_off; j.dst = arena_alloc(n); j.n_in = n;
+    j.copy = cur_copy_;
     if (type == JOB_VALIDATORS) {
         j.chain = cur_chain_;
         validator_jobs_.push_back(j);
@@ -140,15 +151,20 @@ uint32_t SszPlan::wide_records(uint32_t type, uint64_t field_off, uint64_t n, in
         for (auto& c : copies_) if (c.field_off == field_off) c.validators = true;
     } else add_job(0, j);
     PSrc s; s.in_arena = true; s.off = j.dst;
-    return wide_nodes(s, false, n, 0, depth_target, 1);
+    const uint32_t r = wide_nodes(s, false, n, 0, depth_target, 1);
+    cur_copy_ = -1;
+    return r;
 }
 uint32_t SszPlan::wide_pubkeys_with_extra(uint64_t field_off, uint64_t n, int depth_target, uint32_t* extra) {
+    cur_copy_ = copy_of(field_off);
     PJob j;
     j.type = JOB_PUBKEY48; j.src.in_arena = false; j.src.off = field_off; j.dst = arena_alloc(n + 1); j.n_in = n + 1;
     add_job(0, j);
     *extra = uint32_t(j.dst + n);
     PSrc s; s.in_arena = true; s.off = j.dst;
-    return wide_nodes(s, false, n, 0, depth_target, 1);
+    const uint32_t r = wide_nodes(s, false, n, 0, depth_target, 1);
+    cur_copy_ = -1;
+    return r;
 }
 uint64_t SszPlan::h2d_bytes() const {
     uint64_t b = small_words_.size() * 4 + ops_.size() * sizeof(FinOp);
@@ -215,11 +231,12 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
 
     // dirty-path selection lists (host only): per chain, the outputs of job k that lie above the dirty inputs of job k
     std::vector<uint32_t> sel;           // all selection lists back to back
-    struct Launch { const PJob* pj; size_t off; uint32_t n; };
+    struct Launch { const PJob* pj; size_t off; uint32_t n; size_t level; };
     std::vector<Launch> launches;
     if (sparse) {
         for (size_t c = 0; c < chains_.size(); c++) {
             std::vector<uint32_t> cur = (*dirty)[c];
+            size_t level = 0;
             for (auto& ref : chains_[c].jobs) {
                 if (cur.empty()) break;
                 const PJob& pj = ref.first < 0 ? validator_jobs_[ref.second] : stages_[size_t(ref.first)][ref.second];
@@ -233,7 +250,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
                 } else if (pj.type != JOB_REDUCE && pj.type != JOB_VALIDATORS) {
                     return B200_ERR_BAD_ARG;
                 }
-                launches.push_back(Launch{&pj, sel.size(), uint32_t(cur.size())});
+                launches.push_back(Launch{&pj, sel.size(), uint32_t(cur.size()), level++});
                 sel.insert(sel.end(), cur.begin(), cur.end());
             }
         }
@@ -327,7 +344,33 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         // dirty paths of the big lists: per chain, job k recomputes the outputs above the dirty inputs of job k
         B200_CUDA_TRY(cudaMemcpyAsync(selbuf->p, st + off_sel, sel.size() * 4, cudaMemcpyHostToDevice, s));
         const uint32_t* d_sel = static_cast<const uint32_t*>(selbuf->p);
-        for (auto& l : launches) { launch_sparse(materialize(*l.pj), d_arena, d_sel + l.off, l.n, s); e.launches++; }
+        // job k of every chain reads only job k-1 of the SAME chain, so the k-th jobs of all chains share one launch:
+        // the Validator records first (their own kernel), then one fused REDUCE launch per level over all lists
+        size_t n_levels = 0;
+        for (auto& l : launches) n_levels = std::max(n_levels, l.level + 1);
+        for (size_t lev = 0; lev < n_levels; lev++) {
+            SparseDesc sd{};
+            sd.zero_nodes = d_arena; sd.sel = d_sel;
+            uint32_t nb = 0;
+            auto flush = [&]() {
+                if (!sd.njobs) return;
+                sd.block_begin[sd.njobs] = nb;
+                launch_sparse_multi(sd, s); e.launches++;
+                sd.njobs = 0; nb = 0;
+            };
+            for (auto& l : launches) {
+                if (l.level != lev || l.n == 0) continue;
+                if (l.pj->type == JOB_VALIDATORS) { launch_sparse(materialize(*l.pj), d_arena, d_sel + l.off, l.n, s); e.launches++; continue; }
+                if (sd.njobs == kMaxSparseJobs) flush();
+                sd.jobs[sd.njobs] = materialize(*l.pj);
+                sd.sel_begin[sd.njobs] = uint32_t(l.off);
+                sd.n_sel[sd.njobs] = l.n;
+                sd.block_begin[sd.njobs] = nb;
+                nb += (l.n + kStageThreads - 1) / kStageThreads;
+                sd.njobs++;
+            }
+            flush();
+        }
     }
     if (trace) cudaEventRecord(tev[1], s);
     if (!validators_launched)
@@ -335,9 +378,20 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
             if (sparse && pj.chain >= 0) continue;
             launch_validators(materialize(pj), s); e.launches++;
         }
+    // incremental mode: the arena is the resident state's own, so the outputs of a dense job whose staged field did not
+    // change since the previous root are still valid — only fields hit by `changed_host_ranges` are re-hashed
+    std::vector<char> copy_changed(copies_.size(), sparse ? 0 : 1);
+    if (sparse && changed_host_ranges)
+        for (size_t ci = 0; ci < copies_.size(); ci++)
+            for (auto& r : *changed_host_ranges)
+                if (r.first < copies_[ci].src + copies_[ci].nbytes && copies_[ci].src < r.second) copy_changed[ci] = 1;
     for (auto& stage_all : stages_) {
         std::vector<PJob> stage;
-        for (auto& pj : stage_all) if (!(sparse && pj.chain >= 0)) stage.push_back(pj);
+        for (auto& pj : stage_all) {
+            if (sparse && pj.chain >= 0) continue;
+            if (sparse && pj.copy >= 0 && !copy_changed[size_t(pj.copy)]) continue;
+            stage.push_back(pj);
+        }
         // split into launches of at most kMaxJobsPerStage jobs
         for (size_t b = 0; b < stage.size(); b += kMaxJobsPerStage) {
             StageDesc sd{};
@@ -458,8 +512,10 @@ bool parse_beacon_state(const uint8_t* s, size_t len, int preset, StateOffsets& 
 }
 
 // Everything except the five big lists; `big[5]` = their roots (already length-mixed).
+// `chain_vectors`: the four big fixed-size vectors become chains 5..8 (in this order: block_roots, state_roots,
+// randao_mixes, slashings) so that a resident state can re-hash only their dirty paths too.
 static uint32_t assemble_state(SszPlan& p, const uint8_t* s, const StateOffsets& so, const Preset& P,
-                               const uint32_t big[5]) {
+                               const uint32_t big[5], bool chain_vectors = false) {
     std::vector<uint32_t> f(28);
     auto sz = [&](int i) { return size_t(so.var[i + 1] - so.var[i]); };
     f[0] = p.leaf_bytes(s + 0, 8);
@@ -468,8 +524,11 @@ static uint32_t assemble_state(SszPlan& p, const uint8_t* s, const StateOffsets&
     f[3] = p.container({p.leaf_bytes(s + 48, 4), p.leaf_bytes(s + 52, 4), p.leaf_bytes(s + 56, 8)});
     f[4] = p.container({p.leaf_bytes(s + 64, 8), p.leaf_bytes(s + 72, 8), p.leaf(s + 80), p.leaf(s + 112), p.leaf(s + 144)});
     int d_hist = depth_for(P.slots_per_historical_root);
+    if (chain_vectors) p.begin_chain();
     f[5] = p.wide_chunks(p.stage_field(s + so.block_roots, 32 * P.slots_per_historical_root), P.slots_per_historical_root, d_hist);
+    if (chain_vectors) p.begin_chain();
     f[6] = p.wide_chunks(p.stage_field(s + so.state_roots, 32 * P.slots_per_historical_root), P.slots_per_historical_root, d_hist);
+    if (chain_vectors) p.end_chain();
     f[7] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[0], sz(0)), sz(0) / 32, depth_for(P.historical_roots_limit)), sz(0) / 32);
     {
         const uint8_t* e = s + so.eth1_data;
@@ -479,8 +538,11 @@ static uint32_t assemble_state(SszPlan& p, const uint8_t* s, const StateOffsets&
     f[10] = p.leaf_bytes(s + so.eth1_deposit_index, 8);
     f[11] = big[0];
     f[12] = big[1];
+    if (chain_vectors) p.begin_chain();
     f[13] = p.wide_chunks(p.stage_field(s + so.randao_mixes, 32 * P.epochs_per_historical_vector), P.epochs_per_historical_vector, depth_for(P.epochs_per_historical_vector));
+    if (chain_vectors) p.begin_chain();
     f[14] = p.wide_chunks(p.stage_field(s + so.slashings, 8 * P.epochs_per_slashings_vector), P.epochs_per_slashings_vector / 4, depth_for(P.epochs_per_slashings_vector / 4));
+    if (chain_vectors) p.end_chain();
     f[15] = big[2];
     f[16] = big[3];
     f[17] = p.leaf_bytes(s + so.justification_bits, 1);
@@ -557,7 +619,7 @@ int32_t build_beacon_state_plan(SszPlan& p, const uint8_t* s, size_t len, int pr
     p.begin_chain();
     big[4] = p.mix_in_length(p.wide_chunks(p.stage_field(s + so.var[6], sz(6)), (sz(6) + 31) / 32, d_reg - 2), sz(6) / 8);
     p.end_chain();
-    outputs.assign(1, assemble_state(p, s, so, P, big));
+    outputs.assign(1, assemble_state(p, s, so, P, big, true));
     return B200_SUCCESS;
 }
 

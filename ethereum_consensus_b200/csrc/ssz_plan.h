@@ -27,6 +27,7 @@ struct PJob {
     uint64_t n_in = 0;
     uint32_t level = 0, nlev = 0, raw = 0;
     int chain = -1;  // index into SszPlan::chains_ for the jobs of a big list (dirty-path re-hash), else -1
+    int copy = -1;   // index into SszPlan::copies_ of the staged field this job (transitively) reads, else -1
 };
 
 struct HostCopy {
@@ -118,6 +119,8 @@ private:
     std::vector<HostCopy> copies_;
     std::vector<PChain> chains_;
     int cur_chain_ = -1;
+    int cur_copy_ = -1;   // staged field of the wide_* call being planned (stamped on its jobs)
+    int copy_of(uint64_t field_off) const;
     // exchange(): send region, receive region, nodes per rank, world
     uint32_t xch_send_ = 0, xch_recv_ = 0, xch_n_ = 0;
     int xch_world_ = 0;

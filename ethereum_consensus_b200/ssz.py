@@ -104,8 +104,10 @@ def _count_validators(ssz, preset: str) -> int:
     import struct
     hist = 8192 if preset == "mainnet" else 64
     o = 8 + 32 + 8 + 16 + 112 + 2 * 32 * hist + 4 + 72 + 4 + 8   # ... eth1_deposit_index, then the validators offset
-    head = bytes(np.frombuffer(ssz, dtype=np.uint8, count=o + 8)) if not isinstance(ssz, np.ndarray) else bytes(ssz.reshape(-1).view(np.uint8)[: o + 8])
-    v_off, b_off = struct.unpack_from("<II", head, o)
+    nbytes = ssz.nbytes if hasattr(ssz, "nbytes") else len(ssz)
+    if nbytes < o + 8:
+        return 0   # malformed: b200_state_upload_deneb reports it
+    v_off, b_off = struct.unpack("<II", C.string_at(_lib.ptr(ssz) + o, 8))   # any host buffer (bytes, numpy, pinned tensor)
     return (b_off - v_off) // 121
 
 
