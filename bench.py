@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--skip-ssz", action="store_true")
     ap.add_argument("--skip-strong", action="store_true", help="skip the configs[4] strong-scaling batch")
     ap.add_argument("--skip-single", action="store_true", help="skip the single-call latency probe")
+    ap.add_argument("--skip-rlc", action="store_true", help="skip the RLC whole-batch check")
     ap.add_argument("--strong-tuples", type=int, default=2048)
     args = ap.parse_args()
     # Libraries (NCCL's version banner, make, ...) may write to fd 1; the contract is ONE JSON line on stdout from rank 0.
@@ -334,6 +335,32 @@ def main():
                   "h2d_bytes_per_rank": int((hi_t - lo_t) * (48 * K + 128)), "exchange": "ncclAllGather of int32 verdicts inside the library",
                   "checked": "all verdicts equal the constructed expectation on every rank"}
 
+    # ---- RLC whole-batch check (north_star's fused multi-pairing): the all-valid part of the workload, one boolean
+    rlc = None
+    if rank == 0 and not args.skip_rlc:
+        okm = np.nonzero(w["kind"] == 0)[0]
+        rp = pin(w["pks"].reshape(T, K * 48)[okm].reshape(-1).copy())
+        ro = (np.arange(len(okm) + 1, dtype=np.uint64) * K).astype(np.uint32)
+        rm = pin(w["msgs"].reshape(T, 32)[okm].reshape(-1).copy())
+        rs = pin(w["sigs"].reshape(T, 96)[okm].reshape(-1).copy())
+        seed = hashlib.sha256(b"b200/bench/rlc").digest()
+        assert crypto.fast_aggregate_verify_batch_all(rp, ro, rm, rs, seed=seed) is True
+        assert crypto.fast_aggregate_verify_batch_all(pks, off, msgs, sigs, seed=seed) is False   # the adversarial mix
+        r_dev, r_dom = [], []
+        for _ in range(3):
+            flush_l2()
+            assert crypto.fast_aggregate_verify_batch_all(rp, ro, rm, rs, seed=seed) is True
+            r_dev.append(crypto.last_kernel_ms()); r_dom.append(crypto.last_dominant_kernel_ms())
+        p_dev = []
+        for _ in range(3):
+            flush_l2()
+            assert (crypto.fast_aggregate_verify_batch(rp, ro, rm, rs) == 0).all()
+            p_dev.append(crypto.last_kernel_ms())
+        rlc = {"tuples": int(len(okm)), "what": "all-valid subset of the workload; one boolean for the batch (T Miller loops + 1 final exponentiation)",
+               "ms_per_batch_device": sum(r_dev) / 3, "ms_per_key_kernel": sum(r_dom) / 3,
+               "ms_per_tuple_path_same_batch_device": sum(p_dev) / 3,
+               "tuples_per_s_device": len(okm) / (sum(r_dev) / 3 / 1e3)}
+
     # ---- single-call drop-in latency (the per-call path a straight `crypto::fast_aggregate_verify` replacement takes)
     single = None
     if rank == 0 and not args.skip_single:
@@ -448,7 +475,7 @@ def main():
                                        f"{(sample / cpu_dt) * cpu_1t:.1f}x (plain-C restatement of the reference semantics with a dedicated "
                                        "squaring; no assembly: blst is ~1.5-2x faster per core)"},
             "registry_mode": {"ms_per_step": reg_ms, "tuples_per_s": (T / (reg_ms / 1e3)) if reg_ms else None, "registry_load_ms": reg_load_ms},
-            "single_call_latency": single,
+            "single_call_latency": single, "rlc_batch_all": rlc,
             "wall_s_timed_region": t_all,
         })
     if strong is not None:

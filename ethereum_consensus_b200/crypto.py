@@ -38,6 +38,9 @@ _lib.register_protos({
     "b200_registry_load": (C.c_int32, [C.c_void_p, C.c_size_t]),
     "b200_registry_key_codes": (C.c_int32, [C.c_void_p, C.c_size_t]),
     "b200_fast_aggregate_verify_batch_indexed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200_fast_aggregate_verify_batch_all": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]),
+    "b200_fast_aggregate_verify_batch_indexed_all": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]),
+    "b200_fast_aggregate_verify_batch_all_sharded": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]),
     "b200_last_dominant_kernel_ms": (C.c_float, []),
     "b200_fp_selftest": (C.c_int32, [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "b200_measure_int_peak": (C.c_int32, [C.c_int32, C.POINTER(C.c_double)]),
@@ -184,6 +187,27 @@ def fast_aggregate_verify_batch(pks_flat, pk_offsets, msgs32, sigs) -> np.ndarra
     return out[:t]
 
 
+def fast_aggregate_verify_batch_all(pks_flat, pk_offsets, msgs32, sigs, seed: bytes = None, sharded: bool = False) -> bool:
+    """Optimistic whole-batch check by random linear combination (T Miller loops + ONE final exponentiation): True iff
+    every tuple verifies (false accept probability <= 2^-64 over `seed`; None = drawn by the library).  On False ask
+    `fast_aggregate_verify_batch` for the per-tuple codes.  `sharded`: all ranks of the library's communicator share the
+    batch (same arguments and seed on every rank); the Gt / G2 partials travel in one ncclAllGather."""
+    off = np.ascontiguousarray(pk_offsets, dtype=np.uint32)
+    t = len(off) - 1
+    if t < 0 or _nbytes(pks_flat) != 48 * int(off[-1]) or _nbytes(msgs32) != 32 * t or _nbytes(sigs) != 96 * t:
+        raise ValueError("buffer sizes do not match the offsets")
+    if seed is not None and len(seed) != 32:
+        raise ValueError("seed must be 32 bytes")
+    if sharded and seed is None:
+        raise ValueError("the ranks must share the seed")
+    sd = np.frombuffer(bytes(seed), dtype=np.uint8) if seed is not None else None
+    ok = C.c_int32(0)
+    fn = _lib.lib().b200_fast_aggregate_verify_batch_all_sharded if sharded else _lib.lib().b200_fast_aggregate_verify_batch_all
+    _lib.check(fn(_lib.ptr(pks_flat), _lib.ptr(off), _lib.ptr(msgs32), _lib.ptr(sigs), t, _lib.ptr(sd) if sd is not None else 0, C.byref(ok)),
+               "fast_aggregate_verify_batch_all")
+    return bool(ok.value)
+
+
 class Registry:
     """Validated validator public keys resident in HBM (`state.validators[i].public_key` is immutable,
     phase0/validator.rs:10-13): `load` runs key_validate once per key, `verify_batch` names signers by index."""
@@ -208,6 +232,22 @@ class Registry:
         _lib.check(_lib.lib().b200_fast_aggregate_verify_batch_indexed(_lib.ptr(idx), _lib.ptr(off), _lib.ptr(msgs32),
                                                                        _lib.ptr(sigs), t, _lib.ptr(out)), "verify_batch_indexed")
         return out[:t]
+
+
+def _registry_verify_batch_all(self, indices, offsets, msgs32, sigs, seed: bytes = None) -> bool:
+    idx = np.ascontiguousarray(indices, dtype=np.uint32)
+    off = np.ascontiguousarray(offsets, dtype=np.uint32)
+    t = len(off) - 1
+    if t < 0 or len(idx) != int(off[-1]) or _nbytes(msgs32) != 32 * t or _nbytes(sigs) != 96 * t:
+        raise ValueError("indices / offsets / msgs / sigs sizes are inconsistent")
+    sd = np.frombuffer(bytes(seed), dtype=np.uint8) if seed is not None else None
+    ok = C.c_int32(0)
+    _lib.check(_lib.lib().b200_fast_aggregate_verify_batch_indexed_all(_lib.ptr(idx), _lib.ptr(off), _lib.ptr(msgs32), _lib.ptr(sigs), t,
+                                                                       _lib.ptr(sd) if sd is not None else 0, C.byref(ok)), "verify_batch_indexed_all")
+    return bool(ok.value)
+
+
+Registry.verify_batch_all = _registry_verify_batch_all
 
 
 def last_kernel_ms() -> float:

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(32 * kAggWarps) k_g1_aggregate(const G1Aff* __
                                                                   const uint32_t* __restrict__ off, uint32_t n_tuples,
                                                                   G1Aff* __restrict__ agg, G1Pre* __restrict__ agg_pre,
                                                                   int32_t* __restrict__ pk_code,
-                                                                  uint32_t* __restrict__ flags, uint32_t extra_flags) {
+                                                                  uint32_t* __restrict__ flags, uint32_t extra_flags,
+                                                                  G1Jac* __restrict__ agg_jac) {
     __shared__ G1Jac part[kAggWarps][32];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * kAggWarps + warp;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(32 * kAggWarps) k_g1_aggregate(const G1Aff* __
             p.y = s.y;
             p.inf = inf ? 1u : 0u;
             agg_pre[t] = p;
+            if (agg_jac) agg_jac[t] = s;   // the RLC batch check scales the sum itself (bls_rlc.cu)
         } else {
             G1Aff a;
             jac_to_aff(a, part[warp][0]);
@@ -225,11 +227,11 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
 }
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,
                          uint32_t n_tuples, G1Aff* agg, G1Pre* agg_pre, int32_t* pk_code, uint32_t* flags,
-                         uint32_t extra_flags, void* stream) {
+                         uint32_t extra_flags, void* stream, G1Jac* agg_jac) {
     if (!n_tuples) return;
     k_g1_aggregate<<<(n_tuples + kAggWarps - 1) / kAggWarps, 32 * kAggWarps, with_pow_tab(k_g1_aggregate, 32 * kAggWarps),
                      static_cast<cudaStream_t>(stream)>>>(
-        keys, key_codes, index, off, n_tuples, agg, agg_pre, pk_code, flags, extra_flags);
+        keys, key_codes, index, off, n_tuples, agg, agg_pre, pk_code, flags, extra_flags, agg_jac);
 }
 void launch_g1_compress(const G1Aff* p, uint8_t* out48, void* stream) {
     k_g1_compress<<<1, 32, with_pow_tab(k_g1_compress, 32), static_cast<cudaStream_t>(stream)>>>(p, out48);

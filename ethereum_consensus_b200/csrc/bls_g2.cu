@@ -103,15 +103,19 @@ __global__ void __launch_bounds__(32) k_g2_sum_compress(const G2Aff* __restrict_
 }  // namespace
 
 constexpr size_t kPowTab = 0;  // thread-local table here (see above)
+// CTA size of the signature / message kernels: 32 spreads them over all SMs (lowest latency when they run alone, before
+// the per-key kernel); larger CTAs pack them onto few SMs for runs UNDER the per-key kernel (B200_SMALL_ORDER=0)
+static int g_small_cta = kSmallCta;
+void set_small_cta(int threads) { if (threads >= 32 && threads <= 512 && threads % 32 == 0) g_small_cta = threads; }
 
 void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream) {
     if (!n) return;
-    constexpr int threads = kSmallCta;
+    const int threads = g_small_cta;
     k_g2_sig_decode<<<(n + threads - 1) / threads, threads, kPowTab, static_cast<cudaStream_t>(stream)>>>(sigs, n, out, sig_code);
 }
 void launch_hash_to_g2(const uint8_t* msgs, const uint32_t* moff, uint32_t n, G2Aff* out, void* tmp_jac, void* stream) {
     if (!n) return;
-    constexpr int threads = kSmallCta;
+    const int threads = g_small_cta;
     G2Jac* tmp = static_cast<G2Jac*>(tmp_jac);
     k_hash_to_g2_map<<<(2 * n + threads - 1) / threads, threads, kPowTab, static_cast<cudaStream_t>(stream)>>>(msgs, moff, n, tmp);
     k_hash_to_g2_finish<<<(n + threads - 1) / threads, threads, kPowTab, static_cast<cudaStream_t>(stream)>>>(tmp, n, out);

@@ -22,6 +22,7 @@ enum : int32_t { SIG_OK = 0, SIG_NOT_IN_GROUP = -1 };  // >0: blst decode error 
 
 // K1: key_validate every 48-byte public key -> affine point + blst code
 void set_g1_variant(int v);
+void set_small_cta(int threads);
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream);
 // K2: per tuple t, sum the validated keys [off[t], off[t+1]) (or gather through `index` when non-null);
 //     first failing key (in order) decides pk_code[t]
@@ -29,7 +30,12 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
 //     agg_pre != nullptr: write the un-normalised sum for the VM Miller kernel instead of the affine point
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,
                          uint32_t n_tuples, G1Aff* agg, G1Pre* agg_pre, int32_t* pk_code, uint32_t* flags,
-                         uint32_t extra_flags, void* stream);
+                         uint32_t extra_flags, void* stream, G1Jac* agg_jac = nullptr);
+// RLC whole-batch check (bls_rlc.cu): scale per tuple, fold 32 -> 1 per launch, sum -> affine
+void launch_rlc_scale(const G1Jac* agg, const G2Aff* sig, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,
+                      const uint32_t* seed_words, uint64_t t0, uint32_t n, G1Pre* out_g1, G2Jac* out_g2, int32_t* bad, void* stream);
+uint32_t launch_rlc_reduce(const Fp12* f_in, const G2Jac* q_in, uint32_t n, Fp12* f_out, G2Jac* q_out, void* stream);
+void launch_rlc_finish(const G2Jac* q, G2Aff* out, void* stream);
 // K3: decompress + subgroup-check every 96-byte signature
 //     `threads`: CTA size (32 = spread for latency, 512 = pack onto few SMs while the per-key kernel runs)
 void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream);

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <random>
 #include <vector>
 
 #include "bls_kernels.cuh"
@@ -24,6 +25,8 @@ struct BlsState {
     cudaStream_t sb = nullptr, sc = nullptr;  // signatures / messages: run under the per-key kernel
     cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp, gath;
+    // RLC whole-batch check (bls_rlc.cu): Jacobian aggregates, scaled points, reduction ping-pong, zeros, indices, exchange
+    DevBuf rlc_jac, rlc_g1, rlc_q, rlc_fa, rlc_fb, rlc_qa, rlc_qb, rlc_zero, rlc_idx, rlc_misc, rlc_xch;
     PinnedBuf stage;
     G1Aff* d_negg1 = nullptr;
     G1Pre* d_negg1_pre = nullptr;
@@ -33,10 +36,13 @@ struct BlsState {
     float last_dominant_ms = 0.f;
     bool trace = false;          // B200_BLS_TRACE=1: per-phase CUDA-event timings on stderr
     cudaEvent_t ev_t[8] = {nullptr};
-    // B200_SMALL_ORDER (A/B knob): where the signature / message kernels go relative to the per-key kernel K1.
-    // 1 (default) before it, 0 under it on high-priority streams, 2 after it.  Measured on B200 (T=4096, K=512):
-    // 199 / 211 / 201 ms per step — both compete for the same FMA-heavy pipe, so overlap buys nothing.
-    int small_order = 1;
+    // B200_SMALL_ORDER: where the signature / message kernels go relative to the per-key kernel K1: 0 (default) under it on
+    // high-priority streams, 1 before it, 2 after it.  Round 1 measured 211 / 199 / 201 ms per step (T=4096, K=512) and ran
+    // them first; with round 2's K1 (call-based products: a fifth of the code, 12 warps/SM) the overlap wins:
+    // 130.9 / 136.2 ms at T=4096 with 128-thread CTAs, 18.2 / 25.2 ms at T=256 with 32-thread CTAs
+    // (profiles/r2_ab_variants.txt).  B200_SMALL_CTA overrides the CTA size (default: 32 up to 1 024 tuples, else 128).
+    int small_order = 0;
+    int small_cta_override = 0;
     bool use_vm = true;  // lane-parallel pairing kernels (B200_PAIRING_VM=0 selects the one-thread-per-pair kernels)
 };
 
@@ -47,6 +53,7 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         if (const char* v = getenv("B200_PAIRING_VM")) s->use_vm = atoi(v) != 0;
         if (const char* v = getenv("B200_BLS_TRACE")) s->trace = atoi(v) != 0;
         if (const char* v = getenv("B200_SMALL_ORDER")) s->small_order = atoi(v);
+        if (const char* v = getenv("B200_SMALL_CTA")) s->small_cta_override = atoi(v);
         for (auto& ev : s->ev_t) B200_CUDA_TRY(cudaEventCreate(&ev));
         // High priority only matters for B200_SMALL_ORDER=0 (dispatch under the per-key kernel as its CTAs retire).
         int prio_lo = 0, prio = 0;
@@ -93,18 +100,25 @@ constexpr size_t kMaxBatchTuples = size_t(1) << 26;
 // Core: `n_tuples` tuples.  MODE_FAST_AGGREGATE: tuple t sums keys [key_off[t], key_off[t+1]) and checks
 // e(sum, H(msg_t)) e(-g1, sig_t) == 1.  MODE_AGGREGATE: one tuple, pairs (key_i, H(msg_i)) + (-g1, sig).
 // keys: host bytes (strict) or nullptr with `index` (registry gather).  msgs: host bytes + offsets (n_msgs + 1).
+// whole-batch RLC request: when passed, the pairing phase answers ONE boolean for all tuples instead of T codes
+struct RlcReq {
+    const uint8_t* seed32;  // scalars r_t = H(seed || t0 + t)
+    uint64_t t0;            // global index of this call's first tuple (sharded batches)
+    bool exchange;          // all-gather the per-rank (Gt, G2) partials over the library's communicator
+    int32_t all_ok;         // out
+};
 static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint8_t* keys, uint32_t n_keys,
                                const uint32_t* index, uint32_t n_index, const uint32_t* key_off, const uint8_t* msgs,
                                const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
-                               bool force_fail_shape, int32_t* out_codes);
+                               bool force_fail_shape, int32_t* out_codes, RlcReq* rlc);
 // An early error return must not leave work queued on the side streams (they read the caller's host buffers and the
 // engine's grow-only device buffers): drain all three before handing the error back.
 static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* keys, uint32_t n_keys,
                           const uint32_t* index, uint32_t n_index, const uint32_t* key_off, const uint8_t* msgs,
                           const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
-                          bool force_fail_shape, int32_t* out_codes) {
+                          bool force_fail_shape, int32_t* out_codes, RlcReq* rlc = nullptr) {
     const int32_t rc = run_verify_impl(e, s, mode, keys, n_keys, index, n_index, key_off, msgs, msg_off, n_msgs, sigs,
-                                       n_tuples, force_fail_shape, out_codes);
+                                       n_tuples, force_fail_shape, out_codes, rlc);
     if (rc != B200_SUCCESS) {
         cudaStreamSynchronize(e.stream);
         cudaStreamSynchronize(s.sb);
@@ -116,7 +130,8 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
 static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint8_t* keys, uint32_t n_keys,
                                const uint32_t* index, uint32_t n_index, const uint32_t* key_off, const uint8_t* msgs,
                                const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
-                               bool force_fail_shape, int32_t* out_codes) {
+                               bool force_fail_shape, int32_t* out_codes, RlcReq* rlc) {
+    if (rlc && (mode != MODE_FAST_AGGREGATE || !s.use_vm)) return B200_ERR_BAD_ARG;
     const bool registry = (keys == nullptr && index != nullptr);
     const uint32_t T = n_tuples;
     const uint32_t n_g1 = (mode == MODE_FAST_AGGREGATE ? T : n_keys) + 1;  // + (-g1)
@@ -139,6 +154,21 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     B200_CUDA_TRY(s.f.reserve(size_t(n_pairs + 1) * sizeof(Fp12)));
     B200_CUDA_TRY(s.out.reserve(size_t(T + 1) * 4));
     B200_CUDA_TRY(s.h2c_tmp.reserve(size_t(2 * n_msgs + 2) * sizeof(G2Jac)));
+    const uint32_t rlc_world = rlc && rlc->exchange ? uint32_t(comm().world) : 1u;
+    const uint32_t rlc_part = (T + 31) / 32 + rlc_world + 2;   // capacity of one reduction level (+ gathered partials)
+    if (rlc) {
+        B200_CUDA_TRY(s.rlc_jac.reserve(size_t(T + 1) * sizeof(G1Jac)));
+        B200_CUDA_TRY(s.rlc_g1.reserve(size_t(T + 2) * sizeof(G1Pre)));
+        B200_CUDA_TRY(s.rlc_q.reserve(size_t(T + 1) * sizeof(G2Jac)));
+        B200_CUDA_TRY(s.rlc_fa.reserve(size_t(rlc_part) * sizeof(Fp12)));
+        B200_CUDA_TRY(s.rlc_fb.reserve(size_t(rlc_part) * sizeof(Fp12)));
+        B200_CUDA_TRY(s.rlc_qa.reserve(size_t(rlc_part) * sizeof(G2Jac)));
+        B200_CUDA_TRY(s.rlc_qb.reserve(size_t(rlc_part) * sizeof(G2Jac)));
+        B200_CUDA_TRY(s.rlc_zero.reserve(size_t(T + 8) * 4));
+        B200_CUDA_TRY(s.rlc_idx.reserve(size_t(2 * (T + 1)) * 4));
+        B200_CUDA_TRY(s.rlc_misc.reserve(256));
+        B200_CUDA_TRY(s.rlc_xch.reserve(size_t(rlc_world + 1) * (sizeof(Fp12) + sizeof(G2Jac) + 16)));
+    }
 
     // ---- small host-built arrays, one staged copy: [key_off | index | msg_off | g1_idx | g2_idx | pair_tuple | pair_off]
     const uint32_t n_koff = (mode == MODE_FAST_AGGREGATE) ? T + 1 : 2;
@@ -171,7 +201,9 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
         poff[0] = 0; poff[1] = n_pairs;
     }
     const size_t small_bytes = small.size() * 4;
-    B200_CUDA_TRY(s.stage.reserve(small_bytes + size_t(T + 1) * 4 + 64));
+    const size_t kRlcPart = sizeof(Fp12) + sizeof(G2Jac) + 16;   // one rank's exchanged partial: Gt | G2 | bad flag
+    B200_CUDA_TRY(s.stage.reserve(small_bytes + size_t(T + 1) * 4 + 64 +
+                                  (rlc ? 256 + size_t(rlc_world) * kRlcPart + size_t(8 + 2 * (T + 1)) * 4 : 0)));
     B200_CUDA_TRY(s.small.reserve(small_bytes + 64));
     memcpy(s.stage.p, small.data(), small_bytes);
     int32_t* h_out = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(s.stage.p) + ((small_bytes + 15) & ~size_t(15)));
@@ -188,6 +220,7 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
     if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
+    set_small_cta(s.small_cta_override ? s.small_cta_override : (T <= 1024 ? 32 : 128));
     auto launch_small = [&]() -> int32_t {
         B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
         B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
@@ -228,7 +261,8 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
                         (mode == MODE_FAST_AGGREGATE && !s.use_vm) ? d_g1 : nullptr,
                         (mode == MODE_FAST_AGGREGATE && s.use_vm) ? static_cast<G1Pre*>(s.g1pre.p) : nullptr,
                         static_cast<int32_t*>(s.pk_code.p), static_cast<uint32_t*>(s.flags.p),
-                        force_fail_shape ? uint32_t(TUPLE_FLAG_EMPTY) : 0u, sa);
+                        force_fail_shape ? uint32_t(TUPLE_FLAG_EMPTY) : 0u, sa,
+                        rlc ? static_cast<G1Jac*>(s.rlc_jac.p) : nullptr);
     e.launches++;
     const G1Aff* pair_g1 = d_g1;
     if (mode == MODE_FAST_AGGREGATE) {
@@ -248,6 +282,101 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     const uint32_t* d_g2i = d_g1i + n_pairs;
     const uint32_t* d_ptu = d_g2i + n_pairs;
     const uint32_t* d_poff = d_ptu + n_pairs;
+    if (rlc) {
+        // ---- RLC whole-batch check (bls_rlc.cu): T Miller loops + ONE final exponentiation
+        const size_t kPart = kRlcPart;
+        uint8_t* h_x = reinterpret_cast<uint8_t*>(h_out + 16);                    // gathered partials (their bad flags are read on the host)
+        uint32_t* d_zero = static_cast<uint32_t*>(s.rlc_zero.p);  // "every tuple alive" code arrays for the VM kernels
+        uint32_t* d_idx = static_cast<uint32_t*>(s.rlc_idx.p);   // [0..T] identity (g1 / tuple index) | [0..T-1, n_g2] (H_t, then S)
+        uint8_t* d_misc = static_cast<uint8_t*>(s.rlc_misc.p);    // [0,32) seed words | [32,36) bad flag | [64,68) final code
+        G1Pre* d_rg1 = static_cast<G1Pre*>(s.rlc_g1.p);
+        G2Jac* d_rq = static_cast<G2Jac*>(s.rlc_q.p);
+        B200_CUDA_TRY(cudaMemsetAsync(d_zero, 0, size_t(T + 8) * 4, sa));
+        B200_CUDA_TRY(cudaMemsetAsync(d_misc + 32, 0, 96, sa));
+        {   // seed words + index arrays through the pinned staging area (behind the small arrays and the code slots)
+            uint32_t* h = reinterpret_cast<uint32_t*>(h_x + ((size_t(rlc_world) * kPart + 63) & ~size_t(63)));
+            for (int i = 0; i < 8; i++)
+                h[i] = (uint32_t(rlc->seed32[4 * i]) << 24) | (uint32_t(rlc->seed32[4 * i + 1]) << 16) | (uint32_t(rlc->seed32[4 * i + 2]) << 8) | rlc->seed32[4 * i + 3];
+            uint32_t* hi = h + 8;
+            for (uint32_t t = 0; t <= T; t++) { hi[t] = t; hi[T + 1 + t] = t < T ? t : n_g2; }
+            B200_CUDA_TRY(cudaMemcpyAsync(d_misc, h, 32, cudaMemcpyHostToDevice, sa));
+            B200_CUDA_TRY(cudaMemcpyAsync(d_idx, hi, size_t(2 * (T + 1)) * 4, cudaMemcpyHostToDevice, sa));
+        }
+        launch_rlc_scale(static_cast<const G1Jac*>(s.rlc_jac.p), d_g2 + n_msgs, static_cast<const int32_t*>(s.pk_code.p),
+                         static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p),
+                         reinterpret_cast<const uint32_t*>(d_misc), rlc->t0, T, d_rg1, d_rq, reinterpret_cast<int32_t*>(d_misc + 32), sa);
+        B200_CUDA_TRY(cudaMemcpyAsync(d_rg1 + T, s.d_negg1_pre, sizeof(G1Pre), cudaMemcpyDeviceToDevice, sa));
+        if (s.trace) cudaEventRecord(s.ev_t[3], sa);
+        // Miller loops (r_t agg_t, H_t): the lane-parallel VM, one team per tuple
+        launch_vm_miller(d_rg1, d_idx, d_g2, d_idx + T + 1, d_idx, reinterpret_cast<const int32_t*>(d_zero), d_zero,
+                         reinterpret_cast<const int32_t*>(d_zero), T, static_cast<Fp12*>(s.f.p), sa);
+        // warp-shuffle folds: T -> T/32 -> ... -> 1 (Gt product, G2 sum)
+        const Fp12* fi = static_cast<const Fp12*>(s.f.p);
+        const G2Jac* qi = d_rq;
+        Fp12* fbuf[2] = {static_cast<Fp12*>(s.rlc_fa.p), static_cast<Fp12*>(s.rlc_fb.p)};
+        G2Jac* qbuf[2] = {static_cast<G2Jac*>(s.rlc_qa.p), static_cast<G2Jac*>(s.rlc_qb.p)};
+        uint32_t n_cur = T;
+        int pp = 0;
+        do {
+            n_cur = launch_rlc_reduce(fi, qi, n_cur, fbuf[pp], qbuf[pp], sa);
+            e.launches++;
+            fi = fbuf[pp]; qi = qbuf[pp]; pp ^= 1;
+        } while (n_cur > 1);
+        if (rlc->exchange && rlc_world > 1) {
+            // the path's one exchange step: every rank's (Gt partial, G2 partial, bad flag), then the same fold on all
+            uint8_t* x = static_cast<uint8_t*>(s.rlc_xch.p);
+            B200_CUDA_TRY(cudaMemcpyAsync(x, fi, sizeof(Fp12), cudaMemcpyDeviceToDevice, sa));
+            B200_CUDA_TRY(cudaMemcpyAsync(x + sizeof(Fp12), qi, sizeof(G2Jac), cudaMemcpyDeviceToDevice, sa));
+            B200_CUDA_TRY(cudaMemcpyAsync(x + sizeof(Fp12) + sizeof(G2Jac), d_misc + 32, 16, cudaMemcpyDeviceToDevice, sa));
+            int32_t rcx = comm_all_gather(e, x, x + kPart, kPart, sa);
+            if (rcx) return rcx;
+            for (uint32_t r = 0; r < rlc_world; r++) {   // unpack into the fold's input arrays (world <= a few dozen)
+                const uint8_t* src = x + kPart * (1 + r);
+                B200_CUDA_TRY(cudaMemcpyAsync(fbuf[pp] + r, src, sizeof(Fp12), cudaMemcpyDeviceToDevice, sa));
+                B200_CUDA_TRY(cudaMemcpyAsync(qbuf[pp] + r, src + sizeof(Fp12), sizeof(G2Jac), cudaMemcpyDeviceToDevice, sa));
+            }
+            B200_CUDA_TRY(cudaMemcpyAsync(h_x, x + kPart, size_t(rlc_world) * kPart, cudaMemcpyDeviceToHost, sa));   // for the ranks' bad flags
+            fi = fbuf[pp]; qi = qbuf[pp]; pp ^= 1;
+            n_cur = rlc_world;
+            do {
+                n_cur = launch_rlc_reduce(fi, qi, n_cur, fbuf[pp], qbuf[pp], sa);
+                e.launches++;
+                fi = fbuf[pp]; qi = qbuf[pp]; pp ^= 1;
+            } while (n_cur > 1);
+        }
+        // last pair (-g1, S) and the single final exponentiation
+        launch_rlc_finish(qi, d_g2 + n_g2, sa);
+        Fp12* d_fin = fbuf[pp];   // [0] = Gt product, [1] = Miller value of the signature side
+        B200_CUDA_TRY(cudaMemcpyAsync(d_fin, fi, sizeof(Fp12), cudaMemcpyDeviceToDevice, sa));
+        launch_vm_miller(d_rg1, d_idx + T, d_g2, d_idx + 2 * T + 1, d_zero, reinterpret_cast<const int32_t*>(d_zero), d_zero,
+                         reinterpret_cast<const int32_t*>(d_zero), 1, d_fin + 1, sa);
+        launch_vm_final(d_fin, d_zero, reinterpret_cast<const int32_t*>(d_zero), d_zero, reinterpret_cast<const int32_t*>(d_zero), 1,
+                        reinterpret_cast<int32_t*>(d_misc + 64), sa);
+        e.launches += 5;
+        B200_CUDA_TRY(cudaEventRecord(s.ev_k1, sa));
+        B200_CUDA_TRY(cudaGetLastError());
+        B200_CUDA_TRY(cudaMemcpyAsync(h_out, d_misc + 32, 64, cudaMemcpyDeviceToHost, sa));   // [0] bad, [8] final code
+        B200_CUDA_TRY(cudaStreamSynchronize(sa));
+        B200_CUDA_TRY(cudaStreamSynchronize(sb));
+        B200_CUDA_TRY(cudaStreamSynchronize(sc));
+        B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, s.ev_k0, s.ev_k1));
+        B200_CUDA_TRY(cudaEventElapsedTime(&s.last_dominant_ms, s.ev_d0, s.ev_d1));
+        bool bad = h_out[0] != 0;
+        if (rlc->exchange && rlc_world > 1)
+            for (uint32_t r = 0; r < rlc_world; r++) {
+                int32_t flag;
+                memcpy(&flag, h_x + size_t(r) * kPart + sizeof(Fp12) + sizeof(G2Jac), 4);
+                bad = bad || flag != 0;
+            }
+        rlc->all_ok = (!bad && h_out[8] == BLS_SUCCESS) ? 1 : 0;
+        if (s.trace) {
+            float a = 0, g2 = 0;
+            cudaEventElapsedTime(&a, s.ev_t[2], s.ev_k1); cudaEventElapsedTime(&g2, s.ev_k0, s.ev_k1);
+            fprintf(stderr, "[b200 bls rlc] K1 %.2f | scale + T Miller loops + folds + 1 final exponentiation %.2f | total %.2f ms\n",
+                    s.last_dominant_ms, a, g2);
+        }
+        return B200_SUCCESS;
+    }
     if (mode == MODE_FAST_AGGREGATE && s.use_vm) {
         launch_vm_miller(static_cast<const G1Pre*>(s.g1pre.p), d_g1i, d_g2, d_g2i, d_ptu, static_cast<const int32_t*>(s.pk_code.p),
                          static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), n_pairs,
@@ -381,6 +510,105 @@ int32_t b200_fast_aggregate_verify_batch_sharded(const uint8_t* pks_flat, const 
         const size_t rlo = r * base + std::min(r, rem), rcnt = base + (r < rem ? 1 : 0);
         memcpy(out_codes + rlo, h + r * per, rcnt * 4);
     }
+    return B200_SUCCESS;
+}
+
+// ---- RLC whole-batch entry points (bls_rlc.cu) --------------------------------------------------------------------
+static void rlc_seed(const uint8_t* seed32, uint8_t out[32]) {
+    if (seed32) { memcpy(out, seed32, 32); return; }
+    std::random_device rd;   // the scalars must be unpredictable to whoever produced the signatures
+    for (int i = 0; i < 8; i++) { const uint32_t v = rd(); memcpy(out + 4 * i, &v, 4); }
+}
+
+int32_t b200_fast_aggregate_verify_batch_all(const uint8_t* pks_flat, const uint32_t* pk_offsets, const uint8_t* msgs32,
+                                             const uint8_t* sigs, size_t n_tuples, const uint8_t* seed32, int32_t* all_ok) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!all_ok) return B200_ERR_BAD_ARG;
+    if (n_tuples == 0) { *all_ok = 1; return B200_SUCCESS; }
+    if (!pk_offsets || !msgs32 || !sigs || n_tuples > kMaxBatchTuples) return B200_ERR_BAD_ARG;
+    for (size_t t = 0; t < n_tuples; t++)
+        if (pk_offsets[t] > pk_offsets[t + 1]) return B200_ERR_BAD_ARG;
+    const uint32_t nk = pk_offsets[n_tuples];
+    if (nk && !pks_flat) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    std::vector<uint32_t> moff(n_tuples + 1);
+    for (size_t t = 0; t <= n_tuples; t++) moff[t] = uint32_t(32 * t);
+    uint8_t seed[32];
+    rlc_seed(seed32, seed);
+    RlcReq req{seed, 0, false, 0};
+    rc = run_verify(e, *s, MODE_FAST_AGGREGATE, pks_flat, nk, nullptr, 0, pk_offsets, msgs32, moff.data(), uint32_t(n_tuples), sigs,
+                    uint32_t(n_tuples), false, nullptr, &req);
+    if (rc) return rc;
+    *all_ok = req.all_ok;
+    return B200_SUCCESS;
+}
+
+int32_t b200_fast_aggregate_verify_batch_indexed_all(const uint32_t* indices, const uint32_t* offsets, const uint8_t* msgs32,
+                                                     const uint8_t* sigs, size_t n_tuples, const uint8_t* seed32, int32_t* all_ok) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!all_ok) return B200_ERR_BAD_ARG;
+    if (n_tuples == 0) { *all_ok = 1; return B200_SUCCESS; }
+    if (!offsets || !msgs32 || !sigs || n_tuples > kMaxBatchTuples) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    for (size_t t = 0; t < n_tuples; t++)
+        if (offsets[t] > offsets[t + 1]) return B200_ERR_BAD_ARG;
+    const uint32_t ni = offsets[n_tuples];
+    if (ni && !indices) return B200_ERR_BAD_ARG;
+    for (uint32_t i = 0; i < ni; i++)
+        if (indices[i] >= s->reg_n) { e.last_error = "validator index outside the loaded registry"; return B200_ERR_BAD_ARG; }
+    std::vector<uint32_t> moff(n_tuples + 1);
+    for (size_t t = 0; t <= n_tuples; t++) moff[t] = uint32_t(32 * t);
+    static const uint32_t dummy = 0;
+    uint8_t seed[32];
+    rlc_seed(seed32, seed);
+    RlcReq req{seed, 0, false, 0};
+    rc = run_verify(e, *s, MODE_FAST_AGGREGATE, nullptr, 0, indices ? indices : &dummy, ni, offsets, msgs32, moff.data(),
+                    uint32_t(n_tuples), sigs, uint32_t(n_tuples), false, nullptr, &req);
+    if (rc) return rc;
+    *all_ok = req.all_ok;
+    return B200_SUCCESS;
+}
+
+// every rank passes the same batch AND the same seed; each verifies its block, the (Gt, G2) partials are all-gathered and
+// every rank finishes the same single final exponentiation
+int32_t b200_fast_aggregate_verify_batch_all_sharded(const uint8_t* pks_flat, const uint32_t* pk_offsets, const uint8_t* msgs32,
+                                                     const uint8_t* sigs, size_t n_tuples, const uint8_t seed32[32], int32_t* all_ok) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    const Comm& c = comm();
+    if (!c.ready) { e.last_error = "b200_comm_init has not been called"; return B200_ERR_NOT_INITIALIZED; }
+    if (!all_ok || !seed32) return B200_ERR_BAD_ARG;   // the ranks must agree on the scalars: the caller supplies the seed
+    if (n_tuples == 0) { *all_ok = 1; return B200_SUCCESS; }
+    if (!pk_offsets || !msgs32 || !sigs || n_tuples > kMaxBatchTuples) return B200_ERR_BAD_ARG;
+    if (n_tuples < size_t(c.world)) { e.last_error = "fewer tuples than ranks"; return B200_ERR_BAD_ARG; }
+    for (size_t t = 0; t < n_tuples; t++)
+        if (pk_offsets[t] > pk_offsets[t + 1]) return B200_ERR_BAD_ARG;
+    if (pk_offsets[n_tuples] && !pks_flat) return B200_ERR_BAD_ARG;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    const size_t world = size_t(c.world), rank = size_t(c.rank);
+    const size_t base = n_tuples / world, rem = n_tuples % world;
+    const size_t lo = rank * base + std::min(rank, rem), cnt = base + (rank < rem ? 1 : 0);
+    std::vector<uint32_t> koff(cnt + 1), moff(cnt + 1);
+    for (size_t t = 0; t <= cnt; t++) { koff[t] = pk_offsets[lo + t] - pk_offsets[lo]; moff[t] = uint32_t(32 * t); }
+    RlcReq req{seed32, uint64_t(lo), true, 0};
+    rc = run_verify(e, *s, MODE_FAST_AGGREGATE, pks_flat ? pks_flat + size_t(pk_offsets[lo]) * 48 : nullptr, koff[cnt], nullptr, 0,
+                    koff.data(), msgs32 + 32 * lo, moff.data(), uint32_t(cnt), sigs + 96 * lo, uint32_t(cnt), false, nullptr, &req);
+    if (rc) return rc;
+    *all_ok = req.all_ok;
     return B200_SUCCESS;
 }
 

@@ -294,38 +294,42 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     static cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (trace && !tev[0]) for (auto& ev : tev) cudaEventCreate(&ev);
     bool validators_launched = false;
+    // stage launches over the jobs `pick` accepts (at most kMaxJobsPerStage jobs per launch)
+    auto launch_stages = [&](auto&& pick) {
+        for (auto& stage_all : stages_) {
+            std::vector<PJob> stage;
+            for (auto& pj : stage_all) if (pick(pj)) stage.push_back(pj);
+            for (size_t b0 = 0; b0 < stage.size(); b0 += kMaxJobsPerStage) {
+                StageDesc sd{};
+                sd.zero_nodes = d_arena;
+                uint32_t nb = 0;
+                const size_t eidx = std::min(stage.size(), b0 + kMaxJobsPerStage);
+                for (size_t k = b0; k < eidx; k++) {
+                    Job j = materialize(stage[k]);
+                    const uint64_t work = (j.type == JOB_REDUCE) ? ((j.n_in + (uint64_t(1) << j.nlev) - 1) >> j.nlev) : j.n_in;
+                    j.block_begin = nb;
+                    nb += uint32_t((work + kStageThreads - 1) / kStageThreads);
+                    sd.jobs[sd.njobs++] = j;
+                }
+                sd.nblocks = nb;
+                launch_stage(sd, s);
+                e.launches++;
+            }
+        }
+    };
+    auto from_validators = [&](const PJob& pj) { return pj.copy >= 0 && copies_[size_t(pj.copy)].validators; };
+    // One-shot call with a big Validator list: everything else is copied FIRST (a few MB) and hashed while the list
+    // streams in behind it in slices, each slice hashed as soon as it has landed — the kernels hide under the PCIe
+    // transfer (and, in a multi-GPU shard, the small fields under the rank's slice of the list).
+    bool pipelined = false;
+    if (copy == COPY_ALL && !sparse && validator_jobs_.size() == 1)
+        for (auto& c : copies_) pipelined = pipelined || c.validators;
     if (copy != COPY_NONE) {
-        // H2D on the copy stream; the Validator list (85 % of the bytes) goes first, in up to 16 slices, and the compute
-        // stream hashes slice k as soon as its copy has landed: kernels hide under the PCIe transfer.
         cudaStream_t cs = e.copy_stream;
         B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], s));
         B200_CUDA_TRY(cudaStreamWaitEvent(cs, e.ev_copy[16], 0));  // buffers may still be in use by the previous call
         for (auto& c : copies_) {
-            if (!c.validators || validator_jobs_.size() != 1 || copy != COPY_ALL) continue;
-            const PJob& pj = validator_jobs_[0];
-            const uint64_t n = pj.n_in;
-            // up to 16 slices, none smaller than 32 768 records (a multi-GPU shard is 1/world of the list: slices that
-            // cannot fill the 148 SMs would cost more in launches than the overlap buys)
-            const uint64_t n_slices = std::min<uint64_t>(16, std::max<uint64_t>(1, n / 32768));
-            const uint64_t per = ((n + n_slices - 1) / n_slices + kStageThreads - 1) / kStageThreads * kStageThreads;  // whole CTAs per slice
-            int k = 0;
-            for (uint64_t lo = 0; lo < n; lo += per, k++) {
-                const uint64_t cnt = std::min(per, n - lo);
-                B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off + lo * 121, c.src + lo * 121, cnt * 121, cudaMemcpyHostToDevice, cs));
-                B200_CUDA_TRY(cudaEventRecord(e.ev_copy[k], cs));
-                B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[k], 0));
-                Job j = materialize(pj);
-                j.src = d_fields + c.field_off + lo * 121;
-                j.dst = d_arena + (pj.dst + lo) * 8;
-                j.n_in = cnt;
-                launch_validators(j, s);
-                e.launches++;
-            }
-            if (c.nbytes % 32) B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, cs));
-            validators_launched = true;
-        }
-        for (auto& c : copies_) {
-            if (c.validators && validators_launched) continue;
+            if (c.validators && pipelined) continue;
             if (copy == COPY_SMALL_ONLY && c.chain >= 0) continue;
             if (copy == COPY_SMALL_ONLY && changed_host_ranges) {
                 bool hit = false;
@@ -338,6 +342,38 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         }
         B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], cs));
         B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[16], 0));
+        if (pipelined) {
+            launch_stages([&](const PJob& pj) { return !from_validators(pj); });
+            for (auto& c : copies_) {
+                if (!c.validators) continue;
+                const PJob& pj = validator_jobs_[0];
+                const uint64_t n = pj.n_in;
+                // up to 16 slices, none smaller than 32 768 records (a multi-GPU shard is 1/world of the list: slices
+                // that cannot fill the 148 SMs would cost more in launches than the overlap buys)
+                const uint64_t n_slices = std::min<uint64_t>(16, std::max<uint64_t>(1, n / 32768));
+                const uint64_t per = ((n + n_slices - 1) / n_slices + kStageThreads - 1) / kStageThreads * kStageThreads;  // whole CTAs per slice
+                int k = 0;
+                for (uint64_t lo = 0; lo < n; lo += per, k++) {
+                    const uint64_t cnt = std::min(per, n - lo);
+                    B200_CUDA_TRY(cudaMemcpyAsync(d_fields + c.field_off + lo * 121, c.src + lo * 121, cnt * 121, cudaMemcpyHostToDevice, cs));
+                    B200_CUDA_TRY(cudaEventRecord(e.ev_copy[k], cs));
+                    B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[k], 0));
+                    Job j = materialize(pj);
+                    j.src = d_fields + c.field_off + lo * 121;
+                    j.dst = d_arena + (pj.dst + lo) * 8;
+                    j.n_in = cnt;
+                    launch_validators(j, s);
+                    e.launches++;
+                }
+                if (c.nbytes % 32) {
+                    B200_CUDA_TRY(cudaMemsetAsync(d_fields + c.field_off + c.nbytes, 0, c.zero_tail, cs));
+                    B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], cs));
+                    B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[16], 0));
+                }
+                validators_launched = true;
+                break;
+            }
+        }
     }
     if (trace) cudaEventRecord(tev[0], s);
     if (sparse && !sel.empty()) {
@@ -385,31 +421,12 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         for (size_t ci = 0; ci < copies_.size(); ci++)
             for (auto& r : *changed_host_ranges)
                 if (r.first < copies_[ci].src + copies_[ci].nbytes && copies_[ci].src < r.second) copy_changed[ci] = 1;
-    for (auto& stage_all : stages_) {
-        std::vector<PJob> stage;
-        for (auto& pj : stage_all) {
-            if (sparse && pj.chain >= 0) continue;
-            if (sparse && pj.copy >= 0 && !copy_changed[size_t(pj.copy)]) continue;
-            stage.push_back(pj);
-        }
-        // split into launches of at most kMaxJobsPerStage jobs
-        for (size_t b = 0; b < stage.size(); b += kMaxJobsPerStage) {
-            StageDesc sd{};
-            sd.zero_nodes = d_arena;
-            uint32_t nb = 0;
-            size_t eidx = std::min(stage.size(), b + kMaxJobsPerStage);
-            for (size_t k = b; k < eidx; k++) {
-                Job j = materialize(stage[k]);
-                uint64_t work = (j.type == JOB_REDUCE) ? ((j.n_in + (uint64_t(1) << j.nlev) - 1) >> j.nlev) : j.n_in;
-                j.block_begin = nb;
-                nb += uint32_t((work + kStageThreads - 1) / kStageThreads);
-                sd.jobs[sd.njobs++] = j;
-            }
-            sd.nblocks = nb;
-            launch_stage(sd, s);
-            e.launches++;
-        }
-    }
+    launch_stages([&](const PJob& pj) {
+        if (sparse && pj.chain >= 0) return false;
+        if (sparse && pj.copy >= 0 && !copy_changed[size_t(pj.copy)]) return false;
+        if (pipelined && !from_validators(pj)) return false;   // already launched, under the Validator list's transfer
+        return true;
+    });
     if (trace) cudaEventRecord(tev[2], s);
     if (n_local_waves) {
         launch_finisher(d_arena, reinterpret_cast<const FinOp*>(d_plan + off_ops),

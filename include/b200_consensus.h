@@ -199,6 +199,15 @@ B200_API int32_t b200_eth_aggregate_public_keys(const uint8_t* pks_flat, size_t 
  * decompressed and validated in every call, as crypto/bls.rs:119-123 does). */
 B200_API int32_t b200_fast_aggregate_verify_batch(const uint8_t* pks_flat, const uint32_t* pk_offsets, const uint8_t* msgs32,
                                                   const uint8_t* sigs, size_t n_tuples, int32_t* out_codes);
+/* Optimistic WHOLE-BATCH check by random linear combination (north_star: "Miller loops fused across the batch, partial Gt
+ * products reduced with warp shuffles"): *all_ok = 1 iff every tuple of the batch would return 0 above — decided with
+ * T Miller loops and ONE final exponentiation instead of 2T and T:  prod_t e(r_t agg_t, H(msg_t)) * e(-g1, sum_t r_t sig_t) == 1
+ * for 64-bit scalars r_t = SHA-256(seed || t).  Valid batches are always accepted; a batch with an invalid tuple is
+ * accepted with probability <= 2^-64 over the seed (seed32 == NULL: the library draws one from the OS; tests pass a fixed
+ * seed).  This is the normal-case path of process_block (every signature of a block is expected to verify); on
+ * *all_ok == 0 the caller asks b200_fast_aggregate_verify_batch, which remains the only source of per-tuple codes. */
+B200_API int32_t b200_fast_aggregate_verify_batch_all(const uint8_t* pks_flat, const uint32_t* pk_offsets, const uint8_t* msgs32,
+                                                      const uint8_t* sigs, size_t n_tuples, const uint8_t* seed32, int32_t* all_ok);
 /* Registry mode: validate the (append-only, immutable-pubkey) validator registry once, keep the affine keys in
  * HBM, then verify tuples that name their signers by validator index.  Same per-tuple codes as the strict path. */
 B200_API int32_t b200_registry_load(const uint8_t* pks_flat, size_t n);
@@ -206,6 +215,15 @@ B200_API int32_t b200_registry_key_codes(int32_t* out_codes, size_t n);
 B200_API int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indices, const uint32_t* offsets,
                                                           const uint8_t* msgs32, const uint8_t* sigs, size_t n_tuples,
                                                           int32_t* out_codes);
+/* RLC whole-batch check over registry indices, and over all ranks of the communicator: every rank passes the same batch
+ * and the same (non-NULL) seed, verifies its block, and ONE ncclAllGather moves the per-rank Gt partial (576 B) and G2
+ * partial (288 B); every rank then finishes the same final exponentiation and returns the same boolean. */
+B200_API int32_t b200_fast_aggregate_verify_batch_indexed_all(const uint32_t* indices, const uint32_t* offsets,
+                                                              const uint8_t* msgs32, const uint8_t* sigs, size_t n_tuples,
+                                                              const uint8_t* seed32, int32_t* all_ok);
+B200_API int32_t b200_fast_aggregate_verify_batch_all_sharded(const uint8_t* pks_flat, const uint32_t* pk_offsets,
+                                                              const uint8_t* msgs32, const uint8_t* sigs, size_t n_tuples,
+                                                              const uint8_t seed32[32], int32_t* all_ok);
 /* Device time (ms) of the dominant kernel (per-key validation) of the last BLS call. */
 B200_API float b200_last_dominant_kernel_ms(void);
 /* Measured integer-pipe peak on this device, 1e9 ops/s: kind 0 IMAD.WIDE.U32 (Montgomery multiply-add), 1 IMAD.U32,

@@ -58,6 +58,19 @@ for reps in (1, 3):
     assert got.tolist() == [c["code"] for c in cs], got.tolist()
 one = parallel.sharded_verify_batch(pks[: 48 * int(off[1])], off[:2], msgs[:32], sigs[:96])   # fewer tuples than ranks
 assert one.tolist() == [cases[0]["code"]]
+# ---- RLC whole-batch check over both ranks: Gt / G2 partials travel in one ncclAllGather
+import hashlib  # noqa: E402
+good = [c for c in cases if c["code"] == 0] * 3
+gp = np.frombuffer(b"".join(bytes.fromhex(p) for c in good for p in c["pks"]), dtype=np.uint8)
+go = np.cumsum([0] + [len(c["pks"]) for c in good]).astype(np.uint32)
+gm = np.frombuffer(b"".join(bytes.fromhex(c["msg"]) for c in good), dtype=np.uint8)
+gs = np.frombuffer(b"".join(bytes.fromhex(c["sig"]) for c in good), dtype=np.uint8).copy()
+seed = hashlib.sha256(b"two ranks").digest()
+assert crypto.fast_aggregate_verify_batch_all(gp, go, gm, gs, seed=seed, sharded=True) is True
+gs_bad = gs.copy(); gs_bad[-96:] = gs[:96]      # the LAST tuple (rank 1's block) carries the first tuple's signature
+assert crypto.fast_aggregate_verify_batch_all(gp, go, gm, gs_bad, seed=seed, sharded=True) is False
+gs_bad = gs.copy(); gs_bad[:96] = gs[-96:]      # ... and a failure in rank 0's block is seen by rank 1 as well
+assert crypto.fast_aggregate_verify_batch_all(gp, go, gm, gs_bad, seed=seed, sharded=True) is False
 mine = np.array([rank * 10 + 1, rank * 10 + 2], dtype=np.int32)
 assert parallel.comm_all_gather_codes(mine).tolist() == [r * 10 + k for r in range(world) for k in (1, 2)]
 assert lib.b200_collective_count() > 0
