@@ -36,6 +36,7 @@ void launch_rlc_scale(const G1Jac* agg, const G2Aff* sig, const int32_t* pk_code
                       const uint32_t* seed_words, uint64_t t0, uint32_t n, G1Pre* out_g1, G2Jac* out_g2, int32_t* bad, void* stream);
 uint32_t launch_rlc_reduce(const Fp12* f_in, const G2Jac* q_in, uint32_t n, Fp12* f_out, G2Jac* q_out, void* stream);
 void launch_rlc_finish(const G2Jac* q, G2Aff* out, void* stream);
+void launch_fp12_one(Fp12* out, void* stream);
 // K3: decompress + subgroup-check every 96-byte signature
 //     `threads`: CTA size (32 = spread for latency, 512 = pack onto few SMs while the per-key kernel runs)
 void launch_g2_sig_decode(const uint8_t* sigs, uint32_t n, G2Aff* out, int32_t* sig_code, void* stream);

@@ -41,41 +41,46 @@ __device__ __forceinline__ uint64_t rlc_scalar(const uint32_t* __restrict__ seed
     return r ? r : 1;
 }
 
-// one thread per tuple: G1Pre of r_t * agg_t, Jacobian r_t * sig_t; a tuple that already failed a per-point check makes
-// the whole batch fail (*bad = 1) — its code comes from the per-tuple path
+// One thread per (tuple, group): the first half of the grid scales the aggregate keys (G1Pre of r_t * agg_t), the second
+// half the signatures (Jacobian r_t * sig_t) — block-uniform roles, so the two scalar multiplications of a tuple run on
+// different SMs at the same time instead of back to back in one thread.  A tuple that already failed a per-point check
+// makes the whole batch fail (*bad = 1) — its code comes from the per-tuple path.
 __global__ void __launch_bounds__(64) k_rlc_scale(const G1Jac* __restrict__ agg, const G2Aff* __restrict__ sig,
                                                    const int32_t* __restrict__ pk_code, const uint32_t* __restrict__ flags,
                                                    const int32_t* __restrict__ sig_code, const uint32_t* __restrict__ seed_words,
-                                                   uint64_t t0, uint32_t n, G1Pre* __restrict__ out_g1, G2Jac* __restrict__ out_g2,
-                                                   int32_t* __restrict__ bad) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   uint64_t t0, uint32_t n, uint32_t blocks_per_role, G1Pre* __restrict__ out_g1,
+                                                   G2Jac* __restrict__ out_g2, int32_t* __restrict__ bad) {
+    const bool g2_role = blockIdx.x >= blocks_per_role;
+    const uint32_t t = (blockIdx.x - (g2_role ? blocks_per_role : 0u)) * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    G2Jac qz;
-    jac_set_inf(qz);
-    G1Pre pz;
-    pz.xz = fp_one(); pz.y = fp_one(); pz.z3 = fp_zero(); pz.inf = 1;
-    if (pk_code[t] != BLS_SUCCESS || flags[t] != 0 || sig_code[t] != SIG_OK) {
-        atomicExch(bad, 1);
-        out_g1[t] = pz; out_g2[t] = qz;   // neutral contributions keep the reductions well defined
-        return;
-    }
+    const bool dead = pk_code[t] != BLS_SUCCESS || flags[t] != 0 || sig_code[t] != SIG_OK;
     const uint64_t r = rlc_scalar(seed_words, t0 + t);
-    const G1Jac a = agg[t];
-    G1Jac ra;
-    jac_mul_u64_jac(ra, a, r);
-    G1Pre p;
-    p.inf = jac_is_inf(ra) ? 1u : 0u;
-    Fp zz;
-    fp_sqr(zz, ra.z);
-    fp_mul(p.z3, zz, ra.z);
-    fp_mul(p.xz, ra.x, ra.z);
-    p.y = ra.y;
-    out_g1[t] = p;
-    const G2Aff s = sig[t];
-    G2Jac rs;
-    if (s.inf) jac_set_inf(rs);
-    else jac_mul_u64(rs, s.x, s.y, r);
-    out_g2[t] = rs;
+    if (!g2_role) {
+        G1Pre p;
+        if (dead) {
+            atomicExch(bad, 1);
+            p.xz = fp_one(); p.y = fp_one(); p.z3 = fp_zero(); p.inf = 1;   // neutral contribution
+        } else {
+            const G1Jac a = agg[t];
+            G1Jac ra;
+            jac_mul_u64_jac(ra, a, r);
+            p.inf = jac_is_inf(ra) ? 1u : 0u;
+            Fp zz;
+            fp_sqr(zz, ra.z);
+            fp_mul(p.z3, zz, ra.z);
+            fp_mul(p.xz, ra.x, ra.z);
+            p.y = ra.y;
+        }
+        out_g1[t] = p;
+    } else {
+        G2Jac rs;
+        jac_set_inf(rs);
+        if (!dead) {
+            const G2Aff s = sig[t];
+            if (!s.inf) jac_mul_u64(rs, s.x, s.y, r);
+        }
+        out_g2[t] = rs;
+    }
 }
 
 // warp-shuffle exchange of a struct of 32-bit words
@@ -88,27 +93,37 @@ __device__ __forceinline__ void shfl_down_words(T& dst, const T& src, int delta)
     for (unsigned k = 0; k < sizeof(T) / 4; k++) d[k] = __shfl_down_sync(0xffffffffu, s[k], delta);
 }
 
-// One warp folds 32 consecutive (Fp12, G2Jac) pairs with a shuffle tree: lane l multiplies in lane l+s's partial for
-// s = 16, 8, 4, 2, 1; lane 0 writes the warp's partial.  Inputs beyond n are the neutral elements.
+// One warp folds 32 consecutive Fp12 values (product) or G2 points (sum) with a shuffle tree: lane l combines lane l+s's
+// partial for s = 16, 8, 4, 2, 1; lane 0 writes the warp's partial.  Inputs beyond n are the neutral elements.
 __global__ void __launch_bounds__(32) k_rlc_reduce(const Fp12* __restrict__ f_in, const G2Jac* __restrict__ q_in, uint32_t n,
                                                     Fp12* __restrict__ f_out, G2Jac* __restrict__ q_out) {
     const uint32_t lane = threadIdx.x, i = blockIdx.x * 32 + lane;
-    Fp12 f = fp12_one();
-    G2Jac q;
-    jac_set_inf(q);
-    if (i < n) { f = f_in[i]; q = q_in[i]; }
+    if (f_in) {   // Gt product (the launch folds either the Miller values or the scaled signatures, never both)
+        Fp12 f = fp12_one();
+        if (i < n) f = f_in[i];
 #pragma unroll 1
-    for (int s = 16; s > 0; s >>= 1) {
-        Fp12 fo;
-        G2Jac qo;
-        shfl_down_words(fo, f, s);
-        shfl_down_words(qo, q, s);
-        if (lane < uint32_t(s)) {
-            fp12_mul(f, f, fo);
-            jac_add(q, q, qo);
+        for (int s = 16; s > 0; s >>= 1) {
+            Fp12 fo;
+            shfl_down_words(fo, f, s);
+            if (lane < uint32_t(s)) fp12_mul(f, f, fo);
         }
+        if (lane == 0) f_out[blockIdx.x] = f;
     }
-    if (lane == 0) { f_out[blockIdx.x] = f; q_out[blockIdx.x] = q; }
+    if (q_in) {   // G2 sum
+        G2Jac q;
+        jac_set_inf(q);
+        if (i < n) q = q_in[i];
+#pragma unroll 1
+        for (int s = 16; s > 0; s >>= 1) {
+            G2Jac qo;
+            shfl_down_words(qo, q, s);
+            if (lane < uint32_t(s)) jac_add(q, q, qo);
+        }
+        if (lane == 0) q_out[blockIdx.x] = q;
+    }
+}
+__global__ void k_fp12_one(Fp12* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = fp12_one();
 }
 
 // the reduced signature sum as an affine point for the last Miller loop (Q = infinity: that pair contributes 1)
@@ -124,8 +139,9 @@ __global__ void k_rlc_finish(const G2Jac* __restrict__ q, G2Aff* __restrict__ ou
 void launch_rlc_scale(const G1Jac* agg, const G2Aff* sig, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,
                       const uint32_t* seed_words, uint64_t t0, uint32_t n, G1Pre* out_g1, G2Jac* out_g2, int32_t* bad, void* stream) {
     if (!n) return;
-    k_rlc_scale<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(agg, sig, pk_code, flags, sig_code, seed_words, t0, n,
-                                                                              out_g1, out_g2, bad);
+    const uint32_t per_role = (n + 63) / 64;
+    k_rlc_scale<<<2 * per_role, 64, 0, static_cast<cudaStream_t>(stream)>>>(agg, sig, pk_code, flags, sig_code, seed_words, t0, n,
+                                                                            per_role, out_g1, out_g2, bad);
 }
 // folds n inputs to ceil(n / 32) partials
 uint32_t launch_rlc_reduce(const Fp12* f_in, const G2Jac* q_in, uint32_t n, Fp12* f_out, G2Jac* q_out, void* stream) {
@@ -133,6 +149,7 @@ uint32_t launch_rlc_reduce(const Fp12* f_in, const G2Jac* q_in, uint32_t n, Fp12
     if (blocks) k_rlc_reduce<<<blocks, 32, 0, static_cast<cudaStream_t>(stream)>>>(f_in, q_in, n, f_out, q_out);
     return blocks;
 }
+void launch_fp12_one(Fp12* out, void* stream) { k_fp12_one<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out); }
 void launch_rlc_finish(const G2Jac* q, G2Aff* out, void* stream) { k_rlc_finish<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(q, out); }
 
 }  // namespace b200

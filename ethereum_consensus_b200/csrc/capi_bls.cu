@@ -307,49 +307,54 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
                          reinterpret_cast<const uint32_t*>(d_misc), rlc->t0, T, d_rg1, d_rq, reinterpret_cast<int32_t*>(d_misc + 32), sa);
         B200_CUDA_TRY(cudaMemcpyAsync(d_rg1 + T, s.d_negg1_pre, sizeof(G1Pre), cudaMemcpyDeviceToDevice, sa));
         if (s.trace) cudaEventRecord(s.ev_t[3], sa);
-        // Miller loops (r_t agg_t, H_t): the lane-parallel VM, one team per tuple
-        launch_vm_miller(d_rg1, d_idx, d_g2, d_idx + T + 1, d_idx, reinterpret_cast<const int32_t*>(d_zero), d_zero,
-                         reinterpret_cast<const int32_t*>(d_zero), T, static_cast<Fp12*>(s.f.p), sa);
-        // warp-shuffle folds: T -> T/32 -> ... -> 1 (Gt product, G2 sum)
-        const Fp12* fi = static_cast<const Fp12*>(s.f.p);
-        const G2Jac* qi = d_rq;
         Fp12* fbuf[2] = {static_cast<Fp12*>(s.rlc_fa.p), static_cast<Fp12*>(s.rlc_fb.p)};
         G2Jac* qbuf[2] = {static_cast<G2Jac*>(s.rlc_qa.p), static_cast<G2Jac*>(s.rlc_qb.p)};
+        // S = sum_t r_t sig_t first (warp-shuffle folds T -> T/32 -> ... -> 1): its pair (-g1, S) then rides in the SAME
+        // Miller launch as the T tuple pairs instead of costing a second, latency-bound launch of one team
+        const G2Jac* qi = d_rq;
         uint32_t n_cur = T;
         int pp = 0;
         do {
-            n_cur = launch_rlc_reduce(fi, qi, n_cur, fbuf[pp], qbuf[pp], sa);
+            n_cur = launch_rlc_reduce(nullptr, qi, n_cur, nullptr, qbuf[pp], sa);
             e.launches++;
-            fi = fbuf[pp]; qi = qbuf[pp]; pp ^= 1;
+            qi = qbuf[pp]; pp ^= 1;
+        } while (n_cur > 1);
+        launch_rlc_finish(qi, d_g2 + n_g2, sa);
+        // T + 1 Miller loops on the lane-parallel VM: (r_t agg_t, H_t) for every tuple and (-g1, S)
+        launch_vm_miller(d_rg1, d_idx, d_g2, d_idx + T + 1, d_zero, reinterpret_cast<const int32_t*>(d_zero), d_zero,
+                         reinterpret_cast<const int32_t*>(d_zero), T + 1, static_cast<Fp12*>(s.f.p), sa);
+        // Gt product of the T + 1 Miller values, again by warp-shuffle folds
+        const Fp12* fi = static_cast<const Fp12*>(s.f.p);
+        n_cur = T + 1;
+        pp = 0;
+        do {
+            n_cur = launch_rlc_reduce(fi, nullptr, n_cur, fbuf[pp], nullptr, sa);
+            e.launches++;
+            fi = fbuf[pp]; pp ^= 1;
         } while (n_cur > 1);
         if (rlc->exchange && rlc_world > 1) {
-            // the path's one exchange step: every rank's (Gt partial, G2 partial, bad flag), then the same fold on all
+            // the path's one exchange step: e(-g1, sum over ranks) = product over ranks, so every rank has already paired
+            // its own partial sum and only the Gt partial (576 B) and the bad flag travel; then the same fold on all ranks
             uint8_t* x = static_cast<uint8_t*>(s.rlc_xch.p);
             B200_CUDA_TRY(cudaMemcpyAsync(x, fi, sizeof(Fp12), cudaMemcpyDeviceToDevice, sa));
-            B200_CUDA_TRY(cudaMemcpyAsync(x + sizeof(Fp12), qi, sizeof(G2Jac), cudaMemcpyDeviceToDevice, sa));
             B200_CUDA_TRY(cudaMemcpyAsync(x + sizeof(Fp12) + sizeof(G2Jac), d_misc + 32, 16, cudaMemcpyDeviceToDevice, sa));
             int32_t rcx = comm_all_gather(e, x, x + kPart, kPart, sa);
             if (rcx) return rcx;
-            for (uint32_t r = 0; r < rlc_world; r++) {   // unpack into the fold's input arrays (world <= a few dozen)
-                const uint8_t* src = x + kPart * (1 + r);
-                B200_CUDA_TRY(cudaMemcpyAsync(fbuf[pp] + r, src, sizeof(Fp12), cudaMemcpyDeviceToDevice, sa));
-                B200_CUDA_TRY(cudaMemcpyAsync(qbuf[pp] + r, src + sizeof(Fp12), sizeof(G2Jac), cudaMemcpyDeviceToDevice, sa));
-            }
+            for (uint32_t r = 0; r < rlc_world; r++)   // unpack into the fold's input array (world <= a few dozen)
+                B200_CUDA_TRY(cudaMemcpyAsync(fbuf[pp] + r, x + kPart * (1 + r), sizeof(Fp12), cudaMemcpyDeviceToDevice, sa));
             B200_CUDA_TRY(cudaMemcpyAsync(h_x, x + kPart, size_t(rlc_world) * kPart, cudaMemcpyDeviceToHost, sa));   // for the ranks' bad flags
-            fi = fbuf[pp]; qi = qbuf[pp]; pp ^= 1;
+            fi = fbuf[pp]; pp ^= 1;
             n_cur = rlc_world;
             do {
-                n_cur = launch_rlc_reduce(fi, qi, n_cur, fbuf[pp], qbuf[pp], sa);
+                n_cur = launch_rlc_reduce(fi, nullptr, n_cur, fbuf[pp], nullptr, sa);
                 e.launches++;
-                fi = fbuf[pp]; qi = qbuf[pp]; pp ^= 1;
+                fi = fbuf[pp]; pp ^= 1;
             } while (n_cur > 1);
         }
-        // last pair (-g1, S) and the single final exponentiation
-        launch_rlc_finish(qi, d_g2 + n_g2, sa);
-        Fp12* d_fin = fbuf[pp];   // [0] = Gt product, [1] = Miller value of the signature side
+        // the single final exponentiation: (Gt product) * 1
+        Fp12* d_fin = fbuf[pp];
         B200_CUDA_TRY(cudaMemcpyAsync(d_fin, fi, sizeof(Fp12), cudaMemcpyDeviceToDevice, sa));
-        launch_vm_miller(d_rg1, d_idx + T, d_g2, d_idx + 2 * T + 1, d_zero, reinterpret_cast<const int32_t*>(d_zero), d_zero,
-                         reinterpret_cast<const int32_t*>(d_zero), 1, d_fin + 1, sa);
+        launch_fp12_one(d_fin + 1, sa);
         launch_vm_final(d_fin, d_zero, reinterpret_cast<const int32_t*>(d_zero), d_zero, reinterpret_cast<const int32_t*>(d_zero), 1,
                         reinterpret_cast<int32_t*>(d_misc + 64), sa);
         e.launches += 5;

@@ -178,6 +178,20 @@ extern "C" HM int hm_fp_mul_emul_matches(const uint32_t* a, const uint32_t* b) {
     return fp_eq(want, got);
 }
 
+// raw outputs of the emulated PTX product (op 0) / square (op 1) WITHOUT the final conditional subtraction: what the lazily
+// reduced per-key path (fpl.cuh) consumes; operands may be anywhere in [0, 2p)
+extern "C" HM void hm_fp_emul_raw(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    if (op == 0) fp_mul_emul_core(out, a, b);
+    else fp_sqr_emul_core(out, a);
+}
+// FpL add / sub / neg on raw limbs (operands and results in [0, 2p))
+extern "C" HM void hm_fpl_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    FpL x, y, r;
+    for (int i = 0; i < 12; i++) { x.v.l[i] = a[i]; y.v.l[i] = b[i]; }
+    if (op == 0) f_add(r, x, y); else if (op == 1) f_sub(r, x, y); else f_neg(r, x);
+    for (int i = 0; i < 12; i++) out[i] = r.v.l[i];
+}
+
 // ---- Fp2 VM (lane-parallel pairing programs) on the host: scheduled program == direct evaluation, bit for bit
 #include "../../ethereum_consensus_b200/csrc/pairing_vm.cuh"
 static void vm_consts(Fp2* c) { for (int i = 0; i < kVmConsts; i++) vm_const_to_mont(c[i], h_vm_consts[i]); }

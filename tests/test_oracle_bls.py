@@ -220,6 +220,36 @@ def test_fp_mul_ptx_emulation(host_math):
         assert host_math.hm_fp_mul_emul_matches(lim(a), lim(b)) == 1
 
 
+def test_lazily_reduced_field_on_operands_up_to_2p(host_math):
+    """fpl.cuh (the per-key kernel's arithmetic): the emulated PTX product / square WITHOUT the final subtraction map
+    [0, 2p) x [0, 2p) into [0, 2p) and are correct modulo p; add / sub / neg stay in [0, 2p)."""
+    host_math.hm_fp_emul_raw.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    host_math.hm_fpl_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rnd = random.Random(12)
+    A12 = C.c_uint32 * 12
+    lim = lambda x: A12(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(12)])  # noqa: E731
+    val = lambda arr: sum(int(arr[i]) << (32 * i) for i in range(12))        # noqa: E731
+    P, R = bo.P, 1 << 384
+    rinv = pow(R, -1, P)
+    edge = [0, 1, P - 1, P, P + 1, 2 * P - 1, 2 * P - 2, (1 << 381), 2 * P - (1 << 200)]
+    cases = [(a, b) for a in edge for b in edge] + [(rnd.randrange(2 * P), rnd.randrange(2 * P)) for _ in range(20000)]
+    out = A12()
+    worst = 0
+    for a, b in cases:
+        host_math.hm_fp_emul_raw(0, lim(a), lim(b), out)
+        r = val(out)
+        assert r < 2 * P and r % P == a * b * rinv % P, (hex(a), hex(b))
+        worst = max(worst, r)
+        host_math.hm_fp_emul_raw(1, lim(a), lim(a), out)
+        r = val(out)
+        assert r < 2 * P and r % P == a * a * rinv % P, hex(a)
+        worst = max(worst, r)
+        host_math.hm_fpl_op(0, lim(a), lim(b), out); r = val(out); assert r < 2 * P and r % P == (a + b) % P
+        host_math.hm_fpl_op(1, lim(a), lim(b), out); r = val(out); assert r < 2 * P and r % P == (a - b) % P
+        host_math.hm_fpl_op(2, lim(a), lim(b), out); r = val(out); assert r < 2 * P and r % P == (-a) % P
+    assert worst < 1.41 * P + 1     # the bound DESIGN.md section 4 derives: a b / R + p < (4p / R) p + p
+
+
 def test_pairing_vm_programs_match_direct_evaluation(host_math):
     """The statically scheduled lane-parallel Miller / final-exponentiation programs (tools/gen_pairing_vm.py), run by
     the product's interpreter on the host, reproduce miller_loop bit for bit and final_exp_is_one's verdict."""
