@@ -25,11 +25,11 @@ __device__ __forceinline__ void vm_run(const uint32_t* __restrict__ code, int n_
                                        const VmRfStrided& rf, uint32_t lane, bool active) {
 #pragma unroll 1
     for (int r = 0; r < n_rounds; r++) {
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(code) + r * kVmTeam + lane);
-        if (active && (w.x & 0xffu) != VM_NOP) {
+        const uint32_t w = __ldg(code + r * kVmTeam + lane);
+        if (active && (w & 0xffu) != VM_NOP) {
             Fp2 res;
-            vm_exec(w.x, w.y, rf, consts, res);
-            rf.store((w.x >> 8) & 0xffu, res);
+            vm_exec(w, rf, consts, res);
+            rf.store((w >> 8) & 0xffu, res);
         }
         __syncwarp();
     }

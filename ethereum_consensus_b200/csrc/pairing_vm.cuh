@@ -8,12 +8,7 @@
 
 namespace b200 {
 
-// opcodes (must match tools/gen_pairing_vm.py).  VM_LIN: r = sum of up to four terms (+-1, +-2, +-3) * (1 or xi) * slot —
-// a whole single-use chain of additions / subtractions / doublings / xi-multiplications in ONE instruction (round 2: the
-// generator fuses such chains; light ops then cost one round per chain, not per op).  VM_FMUL / VM_FSQR: products whose
-// operands are (s0 +- s1) and (s2 +- s3) — the Karatsuba pre-additions ride in the product's own round.
-enum VmOp : uint32_t { VM_NOP = 0, VM_MUL, VM_SQR, VM_MULFP, VM_INV, VM_ADD, VM_SUB, VM_NEG, VM_DBL, VM_CONJ, VM_MULXI, VM_COPY, VM_LDC,
-                       VM_LIN, VM_FMUL, VM_FSQR };
+enum VmOp : uint32_t { VM_NOP = 0, VM_MUL, VM_SQR, VM_MULFP, VM_INV, VM_ADD, VM_SUB, VM_NEG, VM_DBL, VM_CONJ, VM_MULXI, VM_COPY, VM_LDC };
 
 // register-file accessors: dense array of Fp2 (host) or 25-word-strided shared memory (device, bank-conflict free)
 struct VmRfDense {
@@ -21,7 +16,7 @@ struct VmRfDense {
     B200_HD Fp2 load(uint32_t i) const { return p[i]; }
     B200_HD void store(uint32_t i, const Fp2& v) const { p[i] = v; }
 };
-// Slot stride in words.  25 (round 1): scalar LDS/STS, conflict-free for any slot pattern.  24 / 28 (-DB200_VM_SLOT_WORDS=..):
+// Slot stride in words.  25 (default): scalar LDS/STS, conflict-free for any slot pattern.  24 / 28 (-DB200_VM_SLOT_WORDS=..):
 // 16-byte aligned slots moved with 128-bit LDS/STS — 6 + 6 + 6 wide accesses per light op instead of 24 + 24 + 24.
 #if !defined(B200_VM_SLOT_WORDS)
 #define B200_VM_SLOT_WORDS 25
@@ -62,52 +57,24 @@ struct VmRfStrided {
     }
 };
 
-// one LIN / pre-add term: code = sign 8 | xi 4 | magnitude 1..3 (0 = absent)
+// one instruction: result into `res`, returns false for NOP
 template <class RF>
-B200_HD void vm_term(Fp2& acc, bool& have, const RF& rf, uint32_t slot, uint32_t code) {
-    if (!(code & 3u)) return;
-    Fp2 x = rf.load(slot);
-    if (code & 4u) { Fp2 t; fp2_mul_xi(t, x); x = t; }
-    Fp2 t = x;
-    if ((code & 3u) >= 2u) fp2_dbl(t, x);
-    if ((code & 3u) == 3u) fp2_add(t, t, x);
-    if (!have) { if (code & 8u) fp2_neg(acc, t); else acc = t; have = true; }
-    else if (code & 8u) fp2_sub(acc, acc, t);
-    else fp2_add(acc, acc, t);
-}
-
-// one instruction (two words, see pairing_vm_prog.cuh): result into `res`, returns false for NOP
-template <class RF>
-B200_HD bool vm_exec(uint32_t w0, uint32_t w1, const RF& rf, const Fp2* consts, Fp2& res) {
-    const uint32_t op = w0 & 0xffu, s0 = (w0 >> 16) & 0xffu, s1 = w0 >> 24, s2 = w1 & 0xffu, s3 = (w1 >> 8) & 0xffu;
-    const uint32_t c0 = (w1 >> 16) & 0xfu, c1 = (w1 >> 20) & 0xfu, c2 = (w1 >> 24) & 0xfu, c3 = w1 >> 28;
+B200_HD bool vm_exec(uint32_t w, const RF& rf, const Fp2* consts, Fp2& res) {
+    const uint32_t op = w & 0xffu, a = (w >> 16) & 0xffu, b = w >> 24;
     switch (op) {
     case VM_NOP: return false;
-    case VM_MUL: { const Fp2 x = rf.load(s0), y = rf.load(s1); fp2_mul(res, x, y); } break;
-    case VM_SQR: { const Fp2 x = rf.load(s0); fp2_sqr(res, x); } break;
-    case VM_MULFP: { const Fp2 x = rf.load(s0); const Fp k = rf.load(s1).c0; fp2_mul_fp(res, x, k); } break;
-    case VM_INV: { const Fp2 x = rf.load(s0); fp2_inv(res, x); } break;
-    case VM_LIN: {
-        bool have = false;
-        vm_term(res, have, rf, s0, c0); vm_term(res, have, rf, s1, c1); vm_term(res, have, rf, s2, c2); vm_term(res, have, rf, s3, c3);
-    } break;
-    case VM_FMUL: {
-        Fp2 l, r;
-        bool hl = false, hr = false;
-        vm_term(l, hl, rf, s0, c0); vm_term(l, hl, rf, s1, c1);
-        vm_term(r, hr, rf, s2, c2); vm_term(r, hr, rf, s3, c3);
-        fp2_mul(res, l, r);
-    } break;
-    case VM_FSQR: {
-        Fp2 l;
-        bool hl = false;
-        vm_term(l, hl, rf, s0, c0); vm_term(l, hl, rf, s1, c1);
-        fp2_sqr(res, l);
-    } break;
-    case VM_CONJ: { const Fp2 x = rf.load(s0); fp2_conj(res, x); } break;
-    case VM_COPY: res = rf.load(s0); break;
-    case VM_LDC: res = consts[s0]; break;
-    default: return false;   // the unfused light opcodes are no longer emitted
+    case VM_MUL: { const Fp2 x = rf.load(a), y = rf.load(b); fp2_mul(res, x, y); } break;
+    case VM_SQR: { const Fp2 x = rf.load(a); fp2_sqr(res, x); } break;
+    case VM_MULFP: { const Fp2 x = rf.load(a); const Fp k = rf.load(b).c0; fp2_mul_fp(res, x, k); } break;
+    case VM_INV: { const Fp2 x = rf.load(a); fp2_inv(res, x); } break;
+    case VM_ADD: { const Fp2 x = rf.load(a), y = rf.load(b); fp2_add(res, x, y); } break;
+    case VM_SUB: { const Fp2 x = rf.load(a), y = rf.load(b); fp2_sub(res, x, y); } break;
+    case VM_NEG: { const Fp2 x = rf.load(a); fp2_neg(res, x); } break;
+    case VM_DBL: { const Fp2 x = rf.load(a); fp2_dbl(res, x); } break;
+    case VM_CONJ: { const Fp2 x = rf.load(a); fp2_conj(res, x); } break;
+    case VM_MULXI: { const Fp2 x = rf.load(a); fp2_mul_xi(res, x); } break;
+    case VM_COPY: res = rf.load(a); break;
+    default: res = consts[a]; break;  // VM_LDC
     }
     return true;
 }
@@ -118,9 +85,9 @@ inline void vm_run_host(const uint32_t* code, int n_rounds, const Fp2* consts, F
     for (int r = 0; r < n_rounds; r++) {
         Fp2 res[kVmTeam];
         bool live[kVmTeam];
-        for (int l = 0; l < kVmTeam; l++) live[l] = vm_exec(code[2 * (r * kVmTeam + l)], code[2 * (r * kVmTeam + l) + 1], rf, consts, res[l]);
+        for (int l = 0; l < kVmTeam; l++) live[l] = vm_exec(code[r * kVmTeam + l], rf, consts, res[l]);
         for (int l = 0; l < kVmTeam; l++)
-            if (live[l]) rf.store((code[2 * (r * kVmTeam + l)] >> 8) & 0xffu, res[l]);
+            if (live[l]) rf.store((code[r * kVmTeam + l] >> 8) & 0xffu, res[l]);
     }
 }
 

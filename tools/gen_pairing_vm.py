@@ -25,13 +25,10 @@ Z_ABS = bo.Z_ABS
 MIX_LIGHT = False  # True: ready light ops ride in the idle lanes of heavy rounds (measured offline: halves the rounds but doubles the rounds that pay for a product - a loss)
 
 # opcodes (must match pairing_vm.cuh)
-NOP, MUL, SQR, MULFP, INV, ADD, SUB, NEG, DBL, CONJ, MULXI, COPY, LDC, LIN, FMUL, FSQR = range(16)
-HEAVY = {MUL: "mul", SQR: "sqr", MULFP: "mulfp", INV: "inv", FMUL: "mul", FSQR: "sqr"}
+NOP, MUL, SQR, MULFP, INV, ADD, SUB, NEG, DBL, CONJ, MULXI, COPY, LDC = range(13)
+HEAVY = {MUL: "mul", SQR: "sqr", MULFP: "mulfp", INV: "inv"}
 OPNAME = {MUL: "MUL", SQR: "SQR", MULFP: "MULFP", INV: "INV", ADD: "ADD", SUB: "SUB", NEG: "NEG", DBL: "DBL", CONJ: "CONJ",
-          MULXI: "MULXI", COPY: "COPY", LDC: "LDC", LIN: "LIN", FMUL: "FMUL", FSQR: "FSQR"}
-LINEAR = {ADD, SUB, NEG, DBL, MULXI}
-FUSE = True   # fuse single-use chains of light ops into LIN (<= 4 terms, |coef| <= 3, optional xi) and operand pre-adds
-              # of products into FMUL / FSQR: a light op then costs one round per CHAIN instead of one per op
+          MULXI: "MULXI", COPY: "COPY", LDC: "LDC"}
 
 
 # ------------------------------------------------------------------------------------------------ value classes
@@ -90,18 +87,6 @@ class Num:
     def dbl(self): return Num(bo.f2_add(self.v, self.v))
     def conj(self): return Num((self.v[0], -self.v[1]))
     def mulxi(self): return Num((self.v[0] - self.v[1], self.v[0] + self.v[1]))
-
-
-def term_value(x, code):
-    """Num value of one LIN term: code = sign(8) | xi(4) | magnitude(1..3)."""
-    if code & 4:
-        x = x.mulxi()
-    t = x
-    if (code & 3) >= 2:
-        t = x.dbl()
-    if (code & 3) == 3:
-        t = t.add(x)
-    return t.neg() if code & 8 else t
 
 
 # constant table (index -> Fp2 value); index 0 = one
@@ -311,18 +296,11 @@ def final_exp(cx, f1, f2):
     return f12_mul(c, f12_mul(f12_sqr(f), f))
 
 
-# ------------------------------------------------------------------------------------------------ fusion
-def code_of(m, x):
-    """coefficient m * xi^x -> 4-bit code"""
-    assert 1 <= abs(m) <= 3 and x in (0, 1)
-    return (8 if m < 0 else 0) | (4 if x else 0) | abs(m)
-
-
-def fuse(tr, outputs):
-    """Traced two-operand SSA -> list of generic instructions (op, dst, srcs, codes) with single-use chains of linear ops
-    collapsed into LIN and operand pre-adds of products collapsed into FMUL / FSQR."""
+# ------------------------------------------------------------------------------------------------ schedule + allocate
+def schedule(tr, outputs, team, window=None):
     ins = tr.ins
     producer = {d: i for i, (_, d, _, _) in enumerate(ins)}
+    # dead-code elimination from the outputs
     need, stack = set(), [producer[o] for o in outputs if o in producer]
     while stack:
         i = stack.pop()
@@ -335,137 +313,19 @@ def fuse(tr, outputs):
                 if s in producer:
                     stack.append(producer[s])
     idx = sorted(need)
-    uses = {}
-    for i in idx:
-        op, d, a, b = ins[i]
-        if op == LDC:
-            continue
-        srcs = (a,) if op in (SQR, INV, NEG, DBL, CONJ, MULXI, COPY) else (a, b)
-        for s in srcs:
-            uses[s] = uses.get(s, 0) + 1
-    for o in outputs:
-        uses[o] = uses.get(o, 0) + 1000          # outputs must stay materialised
-    form = {}        # value id -> {(leaf, x): m} for values produced by linear ops (their full expansion so far)
-    absorbed = set()
-
-    def leaf_form(v):
-        return {(v, 0): 1}
-
-    def scale(f, m, xi):
-        out = {}
-        for (leaf, x), c in f.items():
-            nx = x + xi
-            if nx > 1:
-                return None
-            out[(leaf, nx)] = out.get((leaf, nx), 0) + c * m
-        return out
-
-    def combine(f, g):
-        out = dict(f)
-        for k, c in g.items():
-            out[k] = out.get(k, 0) + c
-        return {k: c for k, c in out.items() if c != 0}
-
-    def ok(f):
-        return f is not None and 1 <= len(f) <= 4 and all(1 <= abs(c) <= 3 for c in f.values())
-
-    def operand(v, allow):
-        """form of operand v: its producer's form when that producer is a single-use linear op (then it is absorbed)"""
-        if allow and FUSE and v in form and uses.get(v, 0) == 1:
-            return form[v], v
-        return leaf_form(v), None
-
-    out = []
-    for i in idx:
-        op, d, a, b = ins[i]
-        if op == SUB and a == b:                  # x - x: the zero the sparse first Miller value is padded with
-            out.append([LIN, d, (a, a), (code_of(1, 0), code_of(-1, 0))])
-            continue
-        if op in LINEAR:
-            best = None
-            for allow_a, allow_b in ((True, True), (True, False), (False, True), (False, False)):
-                fa, ua = operand(a, allow_a)
-                if op in (ADD, SUB):
-                    fb, ub = operand(b, allow_b)
-                    f = combine(fa, scale(fb, 1 if op == ADD else -1, 0))
-                else:
-                    if allow_b != allow_a:
-                        continue
-                    ub = None
-                    f = scale(fa, {NEG: -1, DBL: 2, MULXI: 1}[op], 1 if op == MULXI else 0)
-                if ok(f):
-                    best = (f, [u for u in (ua, ub) if u is not None])
-                    break
-            if best is None:                      # e.g. x - x: keep the plain op (never happens in these programs)
-                raise ValueError("unfusable linear op")
-            f, used = best
-            for u in used:
-                absorbed.add(u)
-            form[d] = f
-            terms = sorted(f.items(), key=lambda kv: (kv[1] < 0, kv[0]))   # a positive term first when there is one
-            out.append([LIN, d, tuple(k[0] for k, _ in terms), tuple(code_of(c, k[1]) for k, c in terms)])
-        elif op in (MUL, SQR) and FUSE:
-            def side(v):
-                if v in form and uses.get(v, 0) == 1:
-                    f = form[v]
-                    if len(f) <= 2 and all(abs(c) == 1 and k[1] == 0 for k, c in f.items()) and any(c > 0 for c in f.values()):
-                        t = sorted(f.items(), key=lambda kv: (kv[1] < 0, kv[0]))
-                        return [(k[0], c) for k, c in t], v
-                return [(v, 1)], None
-            if op == SQR:
-                ta, ua = side(a)
-                if ua is not None:
-                    absorbed.add(ua)
-                    srcs = tuple(t[0] for t in ta) + (0,) * (2 - len(ta))
-                    codes = tuple(code_of(t[1], 0) for t in ta) + (0,) * (2 - len(ta))
-                    out.append([FSQR, d, srcs, codes])
-                else:
-                    out.append([SQR, d, (a,), ()])
-            else:
-                ta, ua = side(a)
-                tb, ub = side(b)
-                if a == b:                         # never in these programs (squares are traced as SQR)
-                    ta, ua, tb, ub = [(a, 1)], None, [(b, 1)], None
-                if ua is None and ub is None:
-                    out.append([MUL, d, (a, b), ()])
-                else:
-                    for u in (ua, ub):
-                        if u is not None:
-                            absorbed.add(u)
-                    pad = lambda t: t + [(0, 0)] * (2 - len(t))  # noqa: E731
-                    ta, tb = pad(ta), pad(tb)
-                    srcs = (ta[0][0], ta[1][0], tb[0][0], tb[1][0])
-                    codes = tuple(code_of(c, 0) if c else 0 for _, c in (ta[0], ta[1], tb[0], tb[1]))
-                    out.append([FMUL, d, srcs, codes])
-        elif op == LDC:
-            out.append([LDC, d, (), (a,)])
-        elif op in (SQR, INV, CONJ, COPY):
-            out.append([op, d, (a,), ()])
-        else:                                      # MUL (FUSE off), MULFP
-            out.append([op, d, (a, b), ()])
-    return [tuple(x) for x in out if x[1] not in absorbed]
-
-
-def real_srcs(op, srcs, codes):
-    if op == LIN or op == FMUL or op == FSQR:
-        return [s for s, c in zip(srcs, codes) if c]
-    return list(srcs)
-
-
-# ------------------------------------------------------------------------------------------------ schedule + allocate
-def schedule(tr, outputs, team, window=None):
-    ins = fuse(tr, outputs)
-    producer = {ins[i][1]: i for i in range(len(ins))}
-    idx = list(range(len(ins)))
     deps = {}
     users = {i: [] for i in idx}
     for i in idx:
-        op, d, srcs, codes = ins[i]
-        ds = {producer[s] for s in real_srcs(op, srcs, codes) if s in producer}
+        op, d, a, b = ins[i]
+        ds = set()
+        if op != LDC:
+            for s in (a, b):
+                if s in producer:
+                    ds.add(producer[s])
         deps[i] = ds
         for j in ds:
             users[j].append(i)
-    cost = lambda op: {MUL: 3, FMUL: 3.1, SQR: 2, FSQR: 2.05, MULFP: 2, INV: 600}.get(op, 0.05)  # noqa: E731
+    cost = lambda op: {MUL: 3, SQR: 2, MULFP: 2, INV: 600}.get(op, 0.05)  # noqa: E731
     prio = {}
     for i in reversed(idx):
         prio[i] = cost(ins[i][0]) + max((prio[u] for u in users[i]), default=0)
@@ -494,6 +354,8 @@ def schedule(tr, outputs, team, window=None):
             classes.setdefault(cl, []).append(i)
         heavy_classes = [c for c in classes if c != "light"]
         if MIX_LIGHT and heavy_classes:
+            # a heavy round whenever one is possible; lanes the heavy class leaves idle carry ready light ops (they
+            # diverge from the product code, but a light op is ~4 % of a product and would otherwise cost a round)
             cl = max(heavy_classes, key=lambda c: max(prio[i] for i in classes[c]))
             pick = sorted(classes[cl], key=lambda i: -prio[i])[:team]
             if len(pick) < team and "light" in classes:
@@ -519,9 +381,10 @@ def schedule(tr, outputs, team, window=None):
     # ---- slot allocation (a slot freed by its last reader in round r is reusable from round r + 1)
     last_use = {}
     for i in idx:
-        op, d, srcs, codes = ins[i]
-        for s in real_srcs(op, srcs, codes):
-            last_use[s] = max(last_use.get(s, -1), done_round[i])
+        op, d, a, b = ins[i]
+        if op != LDC:
+            for s in (a, b):
+                last_use[s] = max(last_use.get(s, -1), done_round[i])
     for o in outputs:
         last_use[o] = len(rounds) + 1
     slot = {}
@@ -537,7 +400,7 @@ def schedule(tr, outputs, team, window=None):
     for r, pick in enumerate(rounds):
         row = []
         for i in pick:
-            op, d, srcs, codes = ins[i]
+            op, d, a, b = ins[i]
             if free:
                 s = free.pop()
             else:
@@ -546,11 +409,9 @@ def schedule(tr, outputs, team, window=None):
             lu = last_use.get(d, r)
             release.setdefault(lu, []).append(s)
             if op == LDC:
-                row.append((op, s, (), codes))
-            elif op in (LIN, FMUL, FSQR):
-                row.append((op, s, tuple(slot[x] if c else 0 for x, c in zip(srcs, codes)), codes))
+                row.append((op, s, a, 0))
             else:
-                row.append((op, s, tuple(slot[x] for x in srcs), codes))
+                row.append((op, s, slot[a], slot[b]))
         out_rounds.append(row)
         free.extend(release.pop(r, []))
     return out_rounds, slot, nslots
@@ -562,25 +423,18 @@ def run_program(rounds, nslots, inputs):
         rf[k] = Num(v)
     for row in rounds:
         res = []
-        for op, d, s, codes in row:
-            if op == LDC: res.append((d, Num(CONSTS[codes[0]])))
-            elif op == MUL: res.append((d, rf[s[0]].mul(rf[s[1]])))
-            elif op == SQR: res.append((d, rf[s[0]].sqr()))
-            elif op == MULFP: res.append((d, rf[s[0]].mulfp(rf[s[1]])))
-            elif op == INV: res.append((d, rf[s[0]].inv()))
-            elif op == CONJ: res.append((d, rf[s[0]].conj()))
-            elif op == LIN:
-                acc = None
-                for x, c in zip(s, codes):
-                    t = term_value(rf[x], c)
-                    acc = t if acc is None else acc.add(t)
-                res.append((d, acc))
-            elif op in (FMUL, FSQR):
-                def side(x0, c0, x1, c1):
-                    v = term_value(rf[x0], c0)
-                    return v.add(term_value(rf[x1], c1)) if c1 else v
-                left = side(s[0], codes[0], s[1], codes[1])
-                res.append((d, left.sqr() if op == FSQR else left.mul(side(s[2], codes[2], s[3], codes[3]))))
+        for op, d, a, b in row:
+            if op == LDC: res.append((d, Num(CONSTS[a])))
+            elif op == MUL: res.append((d, rf[a].mul(rf[b])))
+            elif op == SQR: res.append((d, rf[a].sqr()))
+            elif op == MULFP: res.append((d, rf[a].mulfp(rf[b])))
+            elif op == INV: res.append((d, rf[a].inv()))
+            elif op == ADD: res.append((d, rf[a].add(rf[b])))
+            elif op == SUB: res.append((d, rf[a].sub(rf[b])))
+            elif op == NEG: res.append((d, rf[a].neg()))
+            elif op == DBL: res.append((d, rf[a].dbl()))
+            elif op == CONJ: res.append((d, rf[a].conj()))
+            elif op == MULXI: res.append((d, rf[a].mulxi()))
             else: raise ValueError(op)
         for d, v in res:                     # all lanes read before any lane of the round writes
             rf[d] = v
@@ -645,8 +499,7 @@ def selfcheck(team, miller, final):
 def emit(team, miller, final):
     out = ["// GENERATED by tools/gen_pairing_vm.py — do not edit.\n#pragma once\n#include <cstdint>\n\nnamespace b200 {\n\n"]
     out.append(f"constexpr int kVmTeam = {team};\n")
-    out.append("// instruction = 2 words: w0 = op | dst << 8 | s0 << 16 | s1 << 24 ; w1 = s2 | s3 << 8 | codes << 16 (4 bits per\n"
-               "// operand: sign 8 | xi 4 | magnitude 1..3, 0 = absent; LDC: s0 = constant index); rounds are kVmTeam instructions (NOP padded)\n")
+    out.append("// instruction word: op | dst << 8 | a << 16 | b << 24 ; rounds are kVmTeam words each (NOP padded)\n")
     def dump(name, prog):
         rounds, nslots, outs = prog
         words = []
@@ -656,18 +509,11 @@ def emit(team, miller, final):
                 heavy += 1
             for k in range(team):
                 if k < len(row):
-                    op, d, s, codes = row[k]
-                    if op == LDC:
-                        s, codes = (codes[0],), ()
-                    s = tuple(s) + (0,) * (4 - len(s))
-                    cbits = 0
-                    for j, c in enumerate(codes):
-                        cbits |= c << (4 * j)
-                    assert max((d,) + s) < 256 and cbits < 65536
-                    words.append(op | (d << 8) | (s[0] << 16) | (s[1] << 24))
-                    words.append(s[2] | (s[3] << 8) | (cbits << 16))
+                    op, d, a, b = row[k]
+                    assert max(d, a, b) < 256
+                    words.append(op | (d << 8) | (a << 16) | (b << 24))
                 else:
-                    words += [NOP, 0]
+                    words.append(NOP)
         out.append(f"constexpr int k{name}Rounds = {len(rounds)};   // {heavy} heavy rounds\n")
         out.append(f"constexpr int k{name}Slots = {nslots};\n")
         out.append(f"constexpr int k{name}Out[6] = {{{', '.join(map(str, outs))}}};\n")
@@ -700,8 +546,7 @@ def main():
         heavy = [r for r in rounds if r and any(o[0] in HEAVY for o in r)]
         util = sum(len(r) for r in heavy) / max(1, len(heavy) * team)
         print(f"{name}: {len(rounds)} rounds ({len(heavy)} heavy, lane utilisation {util:.2f}), {nslots} slots, "
-              f"{sum(len(r) for r in rounds)} instructions ({sum(1 for r in rounds for o in r if o[0] == LIN)} LIN, "
-              f"{sum(1 for r in rounds for o in r if o[0] in (FMUL, FSQR))} fused products)")
+              f"{sum(len(r) for r in rounds)} instructions")
     selfcheck(team, miller, final)
     print("self-check ok; wrote", emit(team, miller, final))
 
