@@ -16,10 +16,12 @@ struct VmRfDense {
     B200_HD Fp2 load(uint32_t i) const { return p[i]; }
     B200_HD void store(uint32_t i, const Fp2& v) const { p[i] = v; }
 };
-// Slot stride in words.  25 (default): scalar LDS/STS, conflict-free for any slot pattern.  24 / 28 (-DB200_VM_SLOT_WORDS=..):
+// Slot stride in words.  28 (default) / 24: 16-byte aligned slots moved with 128-bit LDS/STS; 25 (round 1, -DB200_VM_SLOT_WORDS=25):
+// scalar LDS/STS, conflict-free for any slot pattern.  Measured on B200, T = 4096 (profiles/r2_ab_variants.txt): Miller 8.95 /
+// 8.41 / 8.05 ms and final exponentiation 6.32 / 6.35 / 6.21 ms for 25 / 24 / 28.
 // 16-byte aligned slots moved with 128-bit LDS/STS — 6 + 6 + 6 wide accesses per light op instead of 24 + 24 + 24.
 #if !defined(B200_VM_SLOT_WORDS)
-#define B200_VM_SLOT_WORDS 25
+#define B200_VM_SLOT_WORDS 28
 #endif
 constexpr int kVmSlotWords = B200_VM_SLOT_WORDS;
 struct VmRfStrided {
