@@ -34,9 +34,11 @@ R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 SEED = 0xB200
 # a point of E'(Fp2) outside G2 (iso3(sswu(5+7u)) compressed; produced by oracle/bls_oracle.py, see tests/golden)
 SIG_NOT_IN_GROUP = None  # filled from tests/golden/bls_cases.json
-# LOP3/SHF/IADD3-class SASS instructions per 64-byte pair hash (2 compressions) in the stage kernels; counted by
-# tools/count_sha_sass.py from cuobjdump of the shipped library
-SASS_OPS_PER_PAIR_HASH = 2325
+# integer-arithmetic SASS instructions per 64-byte pair hash (2 compressions): 2 033 LOP3/SHF/IADD3 + 246 adds / moves the
+# compiler places on the FMA pipe (IMAD.IADD, PRMT, ...) — counted by tools/count_sha_sass.py from cuobjdump of the shipped
+# k_validator_roots (8 pair hashes of straight-line code per thread; 2 340 instructions in all); the denominator
+# b200_measure_int_peak(2) is the same kind of mix, which the compiler also spreads over both pipes
+SASS_OPS_PER_PAIR_HASH = 2279
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -488,6 +490,7 @@ def main():
         host = pin(ssz_bytes)
         golden = json.loads((ROOT / "tests" / "golden" / "ssz_roots.json").read_text()).get("mainnet:1048576:default")
         incremental = None
+        shuffle_stats = None
         if world == 1:
             dev = ssz.DeviceBeaconState(host, "mainnet")
             for _ in range(3):
@@ -542,6 +545,27 @@ def main():
                            "writes_per_block": {"participation_flags": int(max(1, N // 32)), "balances": int(min(N, 513)), "validators": int(min(N, 4)),
                                                 "small_fields": 4},
                            "checked_against": "full from-scratch GPU hash of the patched serialization"}
+            # committee shuffling on the resident state: active-index compaction + 90-round shuffle of
+            # the whole registry, the per-epoch step before the BLS hot path; checked against the numpy oracle
+            from ethereum_consensus_b200 import shuffling as shf
+            from oracle import shuffle_oracle as sho
+            sh_seed = hashlib.sha256(b"b200/bench/shuffle").digest()
+            sh_epoch = 1 << 18
+            sh_ms = []
+            for _ in range(4):
+                flush_l2()
+                t0 = time.perf_counter()
+                shuffled = shf.state_shuffled_active_indices(dev, sh_epoch, sh_seed, 90)
+                sh_ms.append(((time.perf_counter() - t0) * 1e3, float(lib.b200_last_kernel_ms())))
+            vo, vl = lay["validators"]
+            t0 = time.perf_counter()
+            act = np.array(sho.get_active_validator_indices(bytes(ssz_bytes[vo: vo + vl]), sh_epoch), dtype=np.uint64)
+            want_sh = sho.shuffled_indices_numpy(act, sh_seed, 90)
+            sh_cpu = (time.perf_counter() - t0) * 1e3
+            assert np.array_equal(shuffled, want_sh), "shuffled active indices differ from the oracle"
+            shuffle_stats = {"validators": N, "active": int(len(act)), "rounds": 90,
+                             "ms_device": min(m[1] for m in sh_ms[1:]), "ms_e2e_incl_d2h_of_indices": min(m[0] for m in sh_ms[1:]),
+                             "cpu_oracle_ms_numpy_1_thread": sh_cpu, "checked_against": "oracle/shuffle_oracle.py (numpy per-index map)"}
             dev.close()
             es = []
             for i in range(args.steps + 2):
@@ -593,7 +617,7 @@ def main():
                            "e2e_ms_from_pinned_host": sum(es) / len(es), "h2d_bytes": int(len(ssz_bytes)),
                            "scaling": "strong" if world > 1 else None,
                            "exchange": None if single_gpu else "one ncclAllGather of 5 x 32 B per rank inside b200_htr_beacon_state_deneb_sharded",
-                           "incremental": incremental,
+                           "incremental": incremental, "shuffling": shuffle_stats if single_gpu else None,
                            "roofline": {"bound": "alu", "unit": "G ALU instructions/s (LOP3/SHF/IADD3 mix)",
                                         "achieved": (ops / (k_ms / 1e3) / 1e9) if (single_gpu and k_ms and ops) else None,
                                         "peak": alu_peak_ssz,

@@ -23,15 +23,19 @@ __global__ void k_vm_consts(const uint32_t* __restrict__ plain, Fp2* __restrict_
 
 __device__ __forceinline__ void vm_run(const uint32_t* __restrict__ code, int n_rounds, const Fp2* __restrict__ consts,
                                        const VmRfStrided& rf, uint32_t lane, bool active) {
+    // the next round's instruction word is fetched while the current round executes: with one or two warps per scheduler
+    // (small batches) the load's latency would otherwise sit on the critical path of every one of the ~2 500 / ~3 800 rounds
+    uint32_t w = __ldg(code + lane);
 #pragma unroll 1
     for (int r = 0; r < n_rounds; r++) {
-        const uint32_t w = __ldg(code + r * kVmTeam + lane);
+        const uint32_t w_next = (r + 1 < n_rounds) ? __ldg(code + (r + 1) * kVmTeam + lane) : 0u;
         if (active && (w & 0xffu) != VM_NOP) {
             Fp2 res;
             vm_exec(w, rf, consts, res);
             rf.store((w >> 8) & 0xffu, res);
         }
         __syncwarp();
+        w = w_next;
     }
 }
 
