@@ -491,6 +491,7 @@ def main():
         golden = json.loads((ROOT / "tests" / "golden" / "ssz_roots.json").read_text()).get("mainnet:1048576:default")
         incremental = None
         shuffle_stats = None
+        resident_sharded = None
         if world == 1:
             dev = ssz.DeviceBeaconState(host, "mainnet")
             for _ in range(3):
@@ -591,6 +592,20 @@ def main():
                 if i >= 3:
                     es.append(max_over_ranks(dt_ms))
                     ks.append(max_over_ranks(float(lib.b200_last_kernel_ms())))
+            # the same state resident across the ranks: kernels + one ncclAllGather, no PCIe traffic
+            sdev = ssz.DeviceBeaconState(host, "mainnet", sharded=True)
+            rs = []
+            for i in range(args.steps + 3):
+                flush_l2()
+                barrier()
+                t0 = time.perf_counter()
+                root_r = sdev.hash_tree_root()
+                barrier()
+                if i >= 3:
+                    rs.append((max_over_ranks((time.perf_counter() - t0) * 1e3), max_over_ranks(float(lib.b200_last_kernel_ms()))))
+            assert root_r == root
+            sdev.close()
+            resident_sharded = {"ms_wall_max_over_ranks": sum(r[0] for r in rs) / len(rs), "ms_device_max_over_ranks": sum(r[1] for r in rs) / len(rs)}
         if args.validators == 1 << 20 and golden:
             assert root.hex() == golden, "hash_tree_root(BeaconState) differs from the hashlib golden root"
         if rank == 0:
@@ -614,6 +629,7 @@ def main():
             line["ssz"] = {"metric": "hash_tree_root(BeaconState) ms", "validators": args.validators, "root": root.hex(),
                            "value_ms_device_resident": k_ms if single_gpu else None,
                            "value_ms_device_sharded": None if single_gpu else k_ms,
+                           "resident_sharded": resident_sharded,
                            "e2e_ms_from_pinned_host": sum(es) / len(es), "h2d_bytes": int(len(ssz_bytes)),
                            "scaling": "strong" if world > 1 else None,
                            "exchange": None if single_gpu else "one ncclAllGather of 5 x 32 B per rank inside b200_htr_beacon_state_deneb_sharded",

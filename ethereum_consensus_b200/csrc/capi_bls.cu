@@ -220,7 +220,6 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
     if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
-    set_small_cta(s.small_cta_override ? s.small_cta_override : (T <= 1024 ? 32 : 128));
     auto launch_small = [&]() -> int32_t {
         B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
         B200_CUDA_TRY(cudaStreamWaitEvent(sc, s.ev_in, 0));
@@ -234,6 +233,8 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
         return B200_SUCCESS;
     };
     const bool have_k1 = !registry && n_keys;
+    // packed CTAs only when there is a big per-key kernel to run under; alone (registry mode, small batches) they spread
+    set_small_cta(s.small_cta_override ? s.small_cta_override : ((have_k1 && s.small_order == 0 && T > 1024) ? 128 : 32));
     if (have_k1 && s.small_order == 1) {   // signatures / messages first, the per-key kernel only afterwards
         int32_t rc = launch_small();
         if (rc) return rc;

@@ -83,6 +83,7 @@ struct b200_state {
     bool small_dirty = false;
     std::vector<std::pair<const uint8_t*, const uint8_t*>> small_ranges;  // patched shadow bytes since the last root
     bool pinned_head = false, pinned_tail = false;
+    bool sharded = false;   // b200_state_upload_deneb_sharded: this rank's slices only; root is a collective, no updates
     ~b200_state() {  // callers hold the engine lock and have selected the device
         if (pinned_head) cudaHostUnregister(shadow);
         if (pinned_tail) cudaHostUnregister(shadow + so.var[7]);
@@ -317,6 +318,8 @@ int32_t b200_state_root(b200_state* h, uint8_t out[32]) {
     int32_t rc = check_ready(e);
     if (rc) return rc;
     if (!h || !h->uploaded || !out) return B200_ERR_BAD_ARG;
+    if (h->sharded)   // every rank of the communicator calls this together: stages | ncclAllGather | finisher
+        return h->plan.run(e, h->arena, h->fields, h->planbuf, COPY_NONE, h->outputs, out);
     rc = replan_if_small_dirty(e, h);  // updates made through b200_state_update_* are honoured here too
     if (rc) return rc;
     rc = h->plan.run(e, h->arena, h->fields, h->planbuf, h->small_dirty ? COPY_SMALL_ONLY : COPY_NONE, h->outputs, out,
@@ -341,7 +344,7 @@ int32_t b200_state_update_elements(b200_state* h, int32_t field, const uint64_t*
     Guard g(e);
     int32_t rc = check_ready(e);
     if (rc) return rc;
-    if (!h || !h->uploaded || field < 0 || field > 4 || (n && (!indices || !values)) || n > 0xffffffffull) return B200_ERR_BAD_ARG;
+    if (!h || !h->uploaded || h->sharded || field < 0 || field > 4 || (n && (!indices || !values)) || n > 0xffffffffull) return B200_ERR_BAD_ARG;
     if (!n) return B200_SUCCESS;
     const uint64_t count = big_count(h, field);
     for (size_t i = 0; i < n; i++)
@@ -371,7 +374,7 @@ int32_t b200_state_update_bytes(b200_state* h, uint64_t ssz_offset, const uint8_
     Guard g(e);
     int32_t rc = check_ready(e);
     if (rc) return rc;
-    if (!h || !h->uploaded || (n && !data) || ssz_offset > h->len || n > h->len - ssz_offset) return B200_ERR_BAD_ARG;
+    if (!h || !h->uploaded || h->sharded || (n && !data) || ssz_offset > h->len || n > h->len - ssz_offset) return B200_ERR_BAD_ARG;
     if (!n) return B200_SUCCESS;
     const uint64_t lo = ssz_offset, hi = ssz_offset + n;
     // (1) the parts outside the big lists: patch the shadow; the variable-size offsets must not change
@@ -487,7 +490,7 @@ int32_t b200_state_shuffled_active_indices(b200_state* h, uint64_t epoch, const 
     Guard g(e);
     int32_t rc = check_ready(e);
     if (rc) return rc;
-    if (!h || !h->uploaded || !seed || !out_n) return B200_ERR_BAD_ARG;
+    if (!h || !h->uploaded || h->sharded || !seed || !out_n) return B200_ERR_BAD_ARG;
     *out_n = 0;
     const uint64_t n = big_count(h, 0);
     if (n == 0) return B200_SUCCESS;
@@ -508,6 +511,30 @@ int32_t b200_state_shuffled_active_indices(b200_state* h, uint64_t epoch, const 
     B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
     B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, e.ev0, e.ev1));
     *out_n = size_t(cnt);
+    return B200_SUCCESS;
+}
+
+// A state resident across the ranks of the communicator: every rank keeps its slices of the five big lists (and all small
+// fields) in HBM; b200_state_root on such a handle is kernels + one ncclAllGather, no PCIe traffic.  Root only: the
+// update / incremental entry points apply to single-GPU handles.
+int32_t b200_state_upload_deneb_sharded(const uint8_t* ssz, size_t len, int32_t preset, b200_state** out_handle) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    if (!ssz || !out_handle) return B200_ERR_BAD_ARG;
+    const Comm& c = comm();
+    if (!c.ready) { e.last_error = "b200_comm_init has not been called"; return B200_ERR_NOT_INITIALIZED; }
+    std::unique_ptr<b200_state> h(new b200_state());
+    rc = build_beacon_state_sharded_plan(h->plan, ssz, len, preset, c.rank, c.world, h->outputs);
+    if (rc) { e.last_error = "sharded state upload: malformed SSZ or world not a power of two"; return rc; }
+    uint8_t root[32];
+    rc = h->plan.run(e, h->arena, h->fields, h->planbuf, COPY_ALL, h->outputs, root);   // uploads + first (collective) hash
+    if (rc) return rc;
+    h->len = len; h->preset = preset;
+    h->sharded = true;
+    h->uploaded = true;
+    *out_handle = h.release();
     return B200_SUCCESS;
 }
 

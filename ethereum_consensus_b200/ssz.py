@@ -114,12 +114,14 @@ def _count_validators(ssz, preset: str) -> int:
 class DeviceBeaconState:
     """A deneb BeaconState resident in HBM: upload once, `hash_tree_root()` costs kernels only."""
 
-    def __init__(self, ssz, preset: str = "mainnet"):
+    def __init__(self, ssz, preset: str = "mainnet", sharded: bool = False):
+        """`sharded`: the state is spread over the ranks of the library's communicator (parallel.comm_init first; every
+        rank constructs it and calls hash_tree_root together; root only)."""
         nbytes = ssz.nbytes if hasattr(ssz, "nbytes") else len(ssz)
         self._h = C.c_void_p()
         self.n_validators = _count_validators(ssz, preset)
-        _rc(_lib.lib().b200_state_upload_deneb(_lib.ptr(ssz), nbytes, _lib.PRESET[preset], C.byref(self._h)),
-            "state_upload")
+        fn = _lib.lib().b200_state_upload_deneb_sharded if sharded else _lib.lib().b200_state_upload_deneb
+        _rc(fn(_lib.ptr(ssz), nbytes, _lib.PRESET[preset], C.byref(self._h)), "state_upload")
 
     def hash_tree_root(self) -> bytes:
         out = _out32()

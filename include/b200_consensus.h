@@ -161,6 +161,10 @@ B200_API uint64_t b200_collective_count(void);
  * exchanged with one ncclAllGather on the engine stream, and the finisher completes the tree on every rank: no host
  * round trip between the phases.  world must be a power of two.  Every rank gets the same `out`. */
 B200_API int32_t b200_htr_beacon_state_deneb_sharded(const uint8_t* ssz, size_t len, int32_t preset, uint8_t out[32]);
+/* The same, resident: every rank uploads its slices (and the small fields) once; b200_state_root on the returned handle is
+ * then a collective of kernels + one ncclAllGather with no PCIe traffic (all ranks call it together; b200_state_free per
+ * rank).  Root only — the update / incremental / shuffling entry points take single-GPU handles. */
+B200_API int32_t b200_state_upload_deneb_sharded(const uint8_t* ssz, size_t len, int32_t preset, b200_state** out_handle);
 
 /* b200_fast_aggregate_verify_batch over all ranks (BASELINE configs[4]: an epoch's attestation batch sharded over
  * 8 GPUs): every rank passes the same T tuples, verifies the contiguous block parallel.tuple_shard(T, world, rank)

@@ -42,6 +42,10 @@ for n in (1, 5, 70_001, 1 << 17):
     want = ssz.hash_tree_root_beacon_state(ser, "mainnet")
     got = parallel.sharded_state_root(ser, "mainnet")
     assert got == want, (n, got.hex(), want.hex())
+    if n == 70_001:   # resident across the ranks: root is kernels + one all-gather
+        dev = ssz.DeviceBeaconState(ser, "mainnet", sharded=True)
+        assert dev.hash_tree_root() == want and dev.hash_tree_root() == want
+        dev.close()
 st = S.synth_state(300, "minimal", n_historical_summaries=3, n_historical_roots=2)
 ser = S.serialize(st)
 assert parallel.sharded_state_root(ser, "minimal") == ssz.hash_tree_root_beacon_state(ser, "minimal")

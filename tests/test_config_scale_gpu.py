@@ -96,6 +96,9 @@ def test_configs2_full_state_root(engine, comm1, oracle_ssz_c):
     assert oracle_ssz_c.orc_htr_beacon_state_deneb(ser.ctypes.data, len(ser), 0, _threads(), out) == 0
     assert out.raw == root
     assert parallel.sharded_state_root(ser, "mainnet") == root          # exchange plumbing at world = 1
+    sdev = ssz.DeviceBeaconState(ser, "mainnet", sharded=True)          # ... and resident across the (one) rank
+    assert sdev.hash_tree_root() == root
+    sdev.close()
     dev = ssz.DeviceBeaconState(ser, "mainnet")
     assert dev.hash_tree_root() == root
     dev.close()
