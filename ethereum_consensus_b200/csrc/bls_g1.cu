@@ -63,12 +63,6 @@ __global__ void __maxnreg__(128) k_g1_validate_r128(const uint8_t* __restrict__ 
                                                     int32_t* __restrict__ codes) {
     g1_validate_body(keys, n, out, codes);
 }
-template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_g1_validate(const uint8_t* __restrict__ keys, uint32_t n,
-                                                                G1Aff* __restrict__ out, int32_t* __restrict__ codes) {
-    g1_validate_body(keys, n, out, codes);
-}
-
 constexpr int kAggWarps = 4;
 
 __global__ void __launch_bounds__(32 * kAggWarps) k_g1_aggregate(const G1Aff* __restrict__ keys,
@@ -207,22 +201,25 @@ static size_t with_pow_tab(K kernel, unsigned threads) {
     if (n_seen < 16) { seen[n_seen] = key; granted[n_seen++] = bytes; }
     return bytes;
 }
-// tuning knob (B200_G1_VARIANT): 7: 384 threads, 168 registers (default); 0: 256 threads, 224 registers; 6: 512 threads, 128 registers;
-// threads x min CTAs/SM = 1: 128x2, 2: 128x3, 3: 256x2, 4: 128x4, 5: 256x1 uncapped
+// tuning knob (B200_G1_VARIANT): 7: 384 threads, 168 registers (default); 0: 256 threads, 224 registers; 6: 512 threads, 128 registers
 static int g_g1_variant = 7;
+static uint32_t g_g1_small_n = 3u * 148u * 384u;   // B200_G1_SMALL_N overrides (0: always 384-thread CTAs)
+void set_g1_small_n(uint32_t n) { g_g1_small_n = n; }
 void set_g1_variant(int v) { if (v >= 0 && v <= 7) g_g1_variant = v; }
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
     if (!n) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (g_g1_variant) {
-    case 1: k_g1_validate<128, 2><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 2>, 128), st>>>(keys, n, out, codes); break;
-    case 2: k_g1_validate<128, 3><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 3>, 128), st>>>(keys, n, out, codes); break;
-    case 3: k_g1_validate<256, 2><<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate<256, 2>, 256), st>>>(keys, n, out, codes); break;
-    case 4: k_g1_validate<128, 4><<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate<128, 4>, 128), st>>>(keys, n, out, codes); break;
-    case 5: k_g1_validate<256, 1><<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate<256, 1>, 256), st>>>(keys, n, out, codes); break;
     case 6: k_g1_validate_r128<<<(n + 511) / 512, 512, with_pow_tab(k_g1_validate_r128, 512), st>>>(keys, n, out, codes); break;
     case 0: k_g1_validate_main<<<(n + 255) / 256, 256, with_pow_tab(k_g1_validate_main, 256), st>>>(keys, n, out, codes); break;
-    default: k_g1_validate_r168<<<(n + 383) / 384, 384, with_pow_tab(k_g1_validate_r168, 384), st>>>(keys, n, out, codes); break;
+    default:
+        // 12 warps per SM either way; below ~3 full waves of 384-thread CTAs the same kernel goes out as three 128-thread
+        // CTAs per SM, so that the last, partial wave spreads over all SMs instead of leaving most of them idle
+        if (n <= g_g1_small_n)
+            k_g1_validate_r168<<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate_r168, 128), st>>>(keys, n, out, codes);
+        else
+            k_g1_validate_r168<<<(n + 383) / 384, 384, with_pow_tab(k_g1_validate_r168, 384), st>>>(keys, n, out, codes);
+        break;
     }
 }
 void launch_g1_aggregate(const G1Aff* keys, const int32_t* key_codes, const uint32_t* index, const uint32_t* off,

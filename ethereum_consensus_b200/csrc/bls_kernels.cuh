@@ -22,6 +22,7 @@ enum : int32_t { SIG_OK = 0, SIG_NOT_IN_GROUP = -1 };  // >0: blst decode error 
 
 // K1: key_validate every 48-byte public key -> affine point + blst code
 void set_g1_variant(int v);
+void set_g1_small_n(uint32_t n);
 void set_small_cta(int threads);
 void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream);
 // K2: per tuple t, sum the validated keys [off[t], off[t+1]) (or gather through `index` when non-null);

@@ -50,6 +50,7 @@ static int32_t bls_state(Engine& e, BlsState** out) {
     if (!e.bls) {
         BlsState* s = new BlsState();
         if (const char* v = getenv("B200_G1_VARIANT")) set_g1_variant(atoi(v));
+        if (const char* v = getenv("B200_G1_SMALL_N")) set_g1_small_n(uint32_t(atol(v)));
         if (const char* v = getenv("B200_PAIRING_VM")) s->use_vm = atoi(v) != 0;
         if (const char* v = getenv("B200_BLS_TRACE")) s->trace = atoi(v) != 0;
         if (const char* v = getenv("B200_SMALL_ORDER")) s->small_order = atoi(v);

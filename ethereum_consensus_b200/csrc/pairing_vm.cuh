@@ -4,7 +4,8 @@
 // Register allocation guarantees that no slot is both read and written in the same round.
 #pragma once
 #include "fp12.cuh"
-#include "pairing_vm_prog.cuh"  // teams of 8 lanes (teams of 16 measured slower on B200: profiles/r1_tuning.md)
+#include "pairing_vm_prog.cuh"    // teams of 8 lanes: the higher throughput (batches that fill the machine)
+#include "pairing_vm_prog16.cuh"  // teams of 16 lanes: the shorter critical path (1 918 / 3 094 rounds instead of 2 493 / 3 842)
 
 namespace b200 {
 
@@ -81,15 +82,35 @@ B200_HD bool vm_exec(uint32_t w, const RF& rf, const Fp2* consts, Fp2& res) {
     return true;
 }
 
+// The two scheduled program pairs behind one name: VmProg<8>, VmProg<16>
+template <int TEAM> struct VmProg;
+template <> struct VmProg<8> {
+    static constexpr int team = 8, miller_rounds = kMillerRounds, miller_slots = kMillerSlots, final_rounds = kFinalRounds, final_slots = kFinalSlots;
+    static constexpr const int* miller_out = kMillerOut;
+    static constexpr const int* final_out = kFinalOut;
+    static const uint32_t* miller_code() { return h_miller_code; }
+    static const uint32_t* final_code() { return h_final_code; }
+    static constexpr size_t miller_code_bytes = sizeof(h_miller_code), final_code_bytes = sizeof(h_final_code);
+};
+template <> struct VmProg<16> {
+    static constexpr int team = 16, miller_rounds = kMillerRounds16, miller_slots = kMillerSlots16, final_rounds = kFinalRounds16, final_slots = kFinalSlots16;
+    static constexpr const int* miller_out = kMillerOut16;
+    static constexpr const int* final_out = kFinalOut16;
+    static const uint32_t* miller_code() { return h_miller_code16; }
+    static const uint32_t* final_code() { return h_final_code16; }
+    static constexpr size_t miller_code_bytes = sizeof(h_miller_code16), final_code_bytes = sizeof(h_final_code16);
+};
+
 // Sequential reference executor (host tests): all lanes of a round read before any writes.
+template <int TEAM>
 inline void vm_run_host(const uint32_t* code, int n_rounds, const Fp2* consts, Fp2* rf_mem) {
     VmRfDense rf{rf_mem};
     for (int r = 0; r < n_rounds; r++) {
-        Fp2 res[kVmTeam];
-        bool live[kVmTeam];
-        for (int l = 0; l < kVmTeam; l++) live[l] = vm_exec(code[r * kVmTeam + l], rf, consts, res[l]);
-        for (int l = 0; l < kVmTeam; l++)
-            if (live[l]) rf.store((code[r * kVmTeam + l] >> 8) & 0xffu, res[l]);
+        Fp2 res[TEAM];
+        bool live[TEAM];
+        for (int l = 0; l < TEAM; l++) live[l] = vm_exec(code[r * TEAM + l], rf, consts, res[l]);
+        for (int l = 0; l < TEAM; l++)
+            if (live[l]) rf.store((code[r * TEAM + l] >> 8) & 0xffu, res[l]);
     }
 }
 

@@ -195,7 +195,9 @@ extern "C" HM void hm_fpl_op(int op, const uint32_t* a, const uint32_t* b, uint3
 // ---- Fp2 VM (lane-parallel pairing programs) on the host: scheduled program == direct evaluation, bit for bit
 #include "../../ethereum_consensus_b200/csrc/pairing_vm.cuh"
 static void vm_consts(Fp2* c) { for (int i = 0; i < kVmConsts; i++) vm_const_to_mont(c[i], h_vm_consts[i]); }
-extern "C" HM int hm_vm_matches_direct(const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b) {
+template <int TEAM>
+static int vm_matches_direct(const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b) {
+    typedef VmProg<TEAM> P;
     Fp2 consts[kVmConsts];
     vm_consts(consts);
     G1Aff p[2]; G2Aff q[2];
@@ -207,10 +209,10 @@ extern "C" HM int hm_vm_matches_direct(const uint8_t* g1a, const uint8_t* g2a, c
         static Fp2 rf[256];
         rf[0].c0 = p[k].x; rf[0].c1 = fp_zero(); rf[1].c0 = p[k].y; rf[1].c1 = fp_zero();
         rf[2].c0 = fp_one(); rf[2].c1 = fp_zero(); rf[3] = q[k].x; rf[4] = q[k].y;   // affine P: (x, y, 1)
-        vm_run_host(h_miller_code, kMillerRounds, consts, rf);
+        vm_run_host<TEAM>(P::miller_code(), P::miller_rounds, consts, rf);
         Fp12& f = viavm[k];
-        f.c0.c0 = rf[kMillerOut[0]]; f.c1.c0 = rf[kMillerOut[1]]; f.c0.c1 = rf[kMillerOut[2]];
-        f.c1.c1 = rf[kMillerOut[3]]; f.c0.c2 = rf[kMillerOut[4]]; f.c1.c2 = rf[kMillerOut[5]];
+        f.c0.c0 = rf[P::miller_out[0]]; f.c1.c0 = rf[P::miller_out[1]]; f.c0.c1 = rf[P::miller_out[2]];
+        f.c1.c1 = rf[P::miller_out[3]]; f.c0.c2 = rf[P::miller_out[4]]; f.c1.c2 = rf[P::miller_out[5]];
         const Fp2* d = &direct[k].c0.c0; const Fp2* v = &viavm[k].c0.c0;
         for (int i = 0; i < 6; i++) if (!fp2_eq(d[i], v[i])) ok = 0;
     }
@@ -224,9 +226,14 @@ extern "C" HM int hm_vm_matches_direct(const uint8_t* g1a, const uint8_t* g2a, c
         rf[6 * k + 0] = fs[k]->c0.c0; rf[6 * k + 1] = fs[k]->c1.c0; rf[6 * k + 2] = fs[k]->c0.c1;
         rf[6 * k + 3] = fs[k]->c1.c1; rf[6 * k + 4] = fs[k]->c0.c2; rf[6 * k + 5] = fs[k]->c1.c2;
     }
-    vm_run_host(h_final_code, kFinalRounds, consts, rf);
-    int is_one = fp2_eq(rf[kFinalOut[0]], fp2_one());
-    for (int i = 1; i < 6; i++) is_one = is_one && fp2_is_zero(rf[kFinalOut[i]]);
+    vm_run_host<TEAM>(P::final_code(), P::final_rounds, consts, rf);
+    int is_one = fp2_eq(rf[P::final_out[0]], fp2_one());
+    for (int i = 1; i < 6; i++) is_one = is_one && fp2_is_zero(rf[P::final_out[i]]);
     if (is_one != want_one) ok = 0;
     return ok | (is_one << 1);
+}
+// both program pairs (teams of 8 and of 16 lanes) must agree with the direct evaluation: 3 = match + pairing product is one
+extern "C" HM int hm_vm_matches_direct(const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b) {
+    const int r8 = vm_matches_direct<8>(g1a, g2a, g1b, g2b), r16 = vm_matches_direct<16>(g1a, g2a, g1b, g2b);
+    return r8 == r16 ? r8 : 0;
 }

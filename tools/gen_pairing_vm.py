@@ -497,8 +497,9 @@ def selfcheck(team, miller, final):
 
 
 def emit(team, miller, final):
+    sfx = "" if team == 8 else str(team)    # the team-8 header owns the unsuffixed names and the shared constant table
     out = ["// GENERATED by tools/gen_pairing_vm.py — do not edit.\n#pragma once\n#include <cstdint>\n\nnamespace b200 {\n\n"]
-    out.append(f"constexpr int kVmTeam = {team};\n")
+    out.append(f"constexpr int kVmTeam{sfx} = {team};\n")
     out.append("// instruction word: op | dst << 8 | a << 16 | b << 24 ; rounds are kVmTeam words each (NOP padded)\n")
     def dump(name, prog):
         rounds, nslots, outs = prog
@@ -514,22 +515,24 @@ def emit(team, miller, final):
                     words.append(op | (d << 8) | (a << 16) | (b << 24))
                 else:
                     words.append(NOP)
-        out.append(f"constexpr int k{name}Rounds = {len(rounds)};   // {heavy} heavy rounds\n")
-        out.append(f"constexpr int k{name}Slots = {nslots};\n")
-        out.append(f"constexpr int k{name}Out[6] = {{{', '.join(map(str, outs))}}};\n")
-        out.append(f"static const uint32_t h_{name.lower()}_code[{len(words)}] = {{\n")
+        out.append(f"constexpr int k{name}Rounds{sfx} = {len(rounds)};   // {heavy} heavy rounds\n")
+        out.append(f"constexpr int k{name}Slots{sfx} = {nslots};\n")
+        out.append(f"constexpr int k{name}Out{sfx}[6] = {{{', '.join(map(str, outs))}}};\n")
+        out.append(f"static const uint32_t h_{name.lower()}_code{sfx}[{len(words)}] = {{\n")
         for i in range(0, len(words), 8):
             out.append("    " + ", ".join(f"0x{w:08x}u" for w in words[i:i + 8]) + ",\n")
         out.append("};\n\n")
     dump("Miller", miller)
     dump("Final", final)
-    out.append(f"constexpr int kVmConsts = {len(CONSTS)};\n")
-    out.append("// constant table in plain integers: 2 x 12 u32 little-endian limbs per Fp2 (converted to Montgomery form at load time)\n")
-    out.append(f"static const uint32_t h_vm_consts[{len(CONSTS)}][24] = {{\n")
-    for c in CONSTS:
-        limbs = [(c[0] >> (32 * i)) & 0xffffffff for i in range(12)] + [(c[1] >> (32 * i)) & 0xffffffff for i in range(12)]
-        out.append("    {" + ", ".join(f"0x{v:08x}u" for v in limbs) + "},\n")
-    out.append("};\n\n}  // namespace b200\n")
+    if team == 8:
+        out.append(f"constexpr int kVmConsts = {len(CONSTS)};\n")
+        out.append("// constant table in plain integers: 2 x 12 u32 little-endian limbs per Fp2 (converted to Montgomery form at load time)\n")
+        out.append(f"static const uint32_t h_vm_consts[{len(CONSTS)}][24] = {{\n")
+        for c in CONSTS:
+            limbs = [(c[0] >> (32 * i)) & 0xffffffff for i in range(12)] + [(c[1] >> (32 * i)) & 0xffffffff for i in range(12)]
+            out.append("    {" + ", ".join(f"0x{v:08x}u" for v in limbs) + "},\n")
+        out.append("};\n\n")
+    out.append("}  // namespace b200\n")
     path = ROOT / "ethereum_consensus_b200" / "csrc" / ("pairing_vm_prog.cuh" if team == 8 else f"pairing_vm_prog{team}.cuh")
     path.write_text("".join(out))
     return path
@@ -538,7 +541,9 @@ def emit(team, miller, final):
 def main():
     team = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     # scheduling windows (Miller, final): measured trade-off between heavy rounds and register-file slots, see
-    # profiles/r1_tuning.md; defaults: team 16 -> (256, 48), team 8 -> (96, 96)
+    # profiles/r1_tuning.md; defaults: team 16 -> (256, 48), team 8 -> (96, 96).  BOTH headers ship: teams of 8 lanes have the
+    # higher throughput (big batches), teams of 16 the shorter critical path (batches too small to fill the machine):
+    #   python tools/gen_pairing_vm.py 8 && python tools/gen_pairing_vm.py 16
     window = int(sys.argv[2]) if len(sys.argv) > 2 else (256 if team == 16 else 96)
     window_final = int(sys.argv[3]) if len(sys.argv) > 3 else (48 if team == 16 else 96)
     miller, final = build(team, window, window_final)
