@@ -137,7 +137,7 @@ static Fp2* g_d_consts = nullptr;
 // Batches with at most this many teams' worth of work run on 16-lane teams: they cannot fill the machine anyway, so the
 // shorter critical path (1 918 / 3 094 rounds instead of 2 493 / 3 842) wins; above it the 8-lane programs' higher
 // throughput does.  B200_VM_TEAM16_MAX overrides (0: never).
-static uint32_t g_team16_max = 1024;
+static uint32_t g_team16_max = 2048;
 
 template <int TEAM>
 static int vm_upload(int slot, cudaStream_t st) {
