@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kThreads) k_shuffle_map(const uint64_t* __rest
 #pragma unroll 1
     for (uint32_t r = 0; r < rounds; r++) {
         const Idx p = Idx(pivots[r]);
-        Idx flip = p + (nn - idx);          // in (0, 2n)
+        Idx flip = p + (nn - idx);          // in (0, 2n): fits u32 for n <= 2^31
         if (flip >= nn) flip -= nn;
         const Idx pos = idx > flip ? idx : flip;
         // bit (pos % 8) of digest byte (pos % 256) / 8 of source block pos / 256; digest kept as big-endian words
@@ -164,7 +164,9 @@ static uint32_t be32h(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint3
 // out_dev[0..n) = shuffled `idx_dev` (nullptr: identity) on the engine stream; all device pointers
 int32_t shuffle_on_device(Engine& e, const uint64_t* idx_dev, uint64_t n, const uint8_t seed[32], uint32_t rounds, uint64_t* out_dev) {
     if (n == 0) return B200_SUCCESS;
-    if (rounds > 255 || n > (uint64_t(1) << 40)) return B200_ERR_BAD_ARG;
+    // the block index of a source hash is a u32 and the table is rounds x n / 8 bytes: 2^31 positions (24 GB at 90 rounds) is
+    // the ceiling of this formulation, three orders of magnitude above any registry
+    if (rounds > 255 || n > (uint64_t(1) << 31)) { e.last_error = "shuffle: more than 255 rounds or 2^31 positions"; return B200_ERR_BAD_ARG; }
     const uint32_t nblk = uint32_t((n + 255) / 256);
     B200_CUDA_TRY(g_sh.sources.reserve(uint64_t(rounds ? rounds : 1) * nblk * 32));
     B200_CUDA_TRY(g_sh.pivots.reserve(256 * 8));
@@ -183,12 +185,8 @@ int32_t shuffle_on_device(Engine& e, const uint64_t* idx_dev, uint64_t n, const 
         e.launches++;
     }
     const unsigned grid = unsigned((n + kThreads - 1) / kThreads);
-    if (n < (uint64_t(1) << 31))
-        k_shuffle_map<uint32_t><<<grid, kThreads, 0, s>>>(idx_dev, n, rounds, nblk, static_cast<const uint32_t*>(g_sh.sources.p),
-                                                          static_cast<const uint64_t*>(g_sh.pivots.p), out_dev);
-    else
-        k_shuffle_map<uint64_t><<<grid, kThreads, 0, s>>>(idx_dev, n, rounds, nblk, static_cast<const uint32_t*>(g_sh.sources.p),
-                                                          static_cast<const uint64_t*>(g_sh.pivots.p), out_dev);
+    k_shuffle_map<uint32_t><<<grid, kThreads, 0, s>>>(idx_dev, n, rounds, nblk, static_cast<const uint32_t*>(g_sh.sources.p),
+                                                      static_cast<const uint64_t*>(g_sh.pivots.p), out_dev);
     e.launches++;
     B200_CUDA_TRY(cudaGetLastError());
     return B200_SUCCESS;

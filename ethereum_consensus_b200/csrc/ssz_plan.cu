@@ -295,7 +295,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     if (trace && !tev[0]) for (auto& ev : tev) cudaEventCreate(&ev);
     bool validators_launched = false;
     // stage launches over the jobs `pick` accepts (at most kMaxJobsPerStage jobs per launch)
-    auto launch_stages = [&](auto&& pick) {
+    auto launch_stages = [&](auto&& pick, cudaStream_t on) {
         for (auto& stage_all : stages_) {
             std::vector<PJob> stage;
             for (auto& pj : stage_all) if (pick(pj)) stage.push_back(pj);
@@ -312,7 +312,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
                     sd.jobs[sd.njobs++] = j;
                 }
                 sd.nblocks = nb;
-                launch_stage(sd, s);
+                launch_stage(sd, on);
                 e.launches++;
             }
         }
@@ -343,7 +343,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], cs));
         B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[16], 0));
         if (pipelined) {
-            launch_stages([&](const PJob& pj) { return !from_validators(pj); });
+            launch_stages([&](const PJob& pj) { return !from_validators(pj); }, s);
             for (auto& c : copies_) {
                 if (!c.validators) continue;
                 const PJob& pj = validator_jobs_[0];
@@ -409,11 +409,24 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         }
     }
     if (trace) cudaEventRecord(tev[1], s);
+    // Full re-hash of a RESIDENT state: the stage chains of everything except the Validator list (five latency-bound
+    // launches over ~0.7 M hashes) run on the idle copy stream UNDER the Validator kernel (8.4 M hashes, throughput-bound)
+    // instead of after it; the list's own upper levels follow once both are done.
+    bool side_stages = false;
+    if (!sparse && copy == COPY_NONE && !validators_launched && validator_jobs_.size() == 1) {
+        cudaStream_t cs = e.copy_stream;
+        B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], s));           // plan upload + earlier work on the compute stream
+        B200_CUDA_TRY(cudaStreamWaitEvent(cs, e.ev_copy[16], 0));
+        launch_stages([&](const PJob& pj) { return !from_validators(pj); }, cs);
+        B200_CUDA_TRY(cudaEventRecord(e.ev_copy[15], cs));
+        side_stages = true;
+    }
     if (!validators_launched)
         for (auto& pj : validator_jobs_) {
             if (sparse && pj.chain >= 0) continue;
             launch_validators(materialize(pj), s); e.launches++;
         }
+    if (side_stages) B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[15], 0));
     // incremental mode: the arena is the resident state's own, so the outputs of a dense job whose staged field did not
     // change since the previous root are still valid — only fields hit by `changed_host_ranges` are re-hashed
     std::vector<char> copy_changed(copies_.size(), sparse ? 0 : 1);
@@ -424,9 +437,9 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     launch_stages([&](const PJob& pj) {
         if (sparse && pj.chain >= 0) return false;
         if (sparse && pj.copy >= 0 && !copy_changed[size_t(pj.copy)]) return false;
-        if (pipelined && !from_validators(pj)) return false;   // already launched, under the Validator list's transfer
+        if ((pipelined || side_stages) && !from_validators(pj)) return false;   // already launched, under the list's transfer / kernel
         return true;
-    });
+    }, s);
     if (trace) cudaEventRecord(tev[2], s);
     if (n_local_waves) {
         launch_finisher(d_arena, reinterpret_cast<const FinOp*>(d_plan + off_ops),
