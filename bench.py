@@ -142,6 +142,7 @@ class ClockSampler:
                 "reasons": [k for k, v in names.items() if bits & v]}
 
 
+from tests import workloads  # noqa: E402
 from tests.workloads import make_bls_workload  # noqa: E402  (the workload generator is shared with the parity tests)
 
 
@@ -165,6 +166,7 @@ def main():
     ap.add_argument("--skip-strong", action="store_true", help="skip the configs[4] strong-scaling batch")
     ap.add_argument("--skip-single", action="store_true", help="skip the single-call latency probe")
     ap.add_argument("--skip-rlc", action="store_true", help="skip the RLC whole-batch check")
+    ap.add_argument("--skip-block", action="store_true", help="skip the configs[3] block signature set")
     ap.add_argument("--strong-tuples", type=int, default=2048)
     args = ap.parse_args()
     # Libraries (NCCL's version banner, make, ...) may write to fd 1; the contract is ONE JSON line on stdout from rank 0.
@@ -393,6 +395,32 @@ def main():
                 assert got == want, (kk, got, want)
             single[f"K={kk}"] = {"ms_per_call": sorted(ts)[len(ts) // 2], "code": want}
 
+    # ---- BASELINE configs[3]: the deneb process_block signature set at spec shape (215 checks), through the host-side
+    # collector, host buffers in, code vector out; strict (every key decompressed + validated) and registry mode
+    blockset = None
+    if rank == 0 and not args.skip_block:
+        breg, rows = workloads.make_deneb_block_plan(orc_bls, threads=host_threads)
+        sset = workloads.collect_block_signature_set(breg, rows)
+        want = [r["expect"] for r in rows]
+        reg_b = crypto.Registry(breg.reshape(-1))
+        blockset = {"checks": len(rows), "keys_named": int(sum(len(e.pubkeys) for e in sset.entries)),
+                    "what": "1 proposer + 1 randao + 32 slashing headers + 4 x K=2048 + 128 x K=512 + 16 deposits + 16 exits + 16 changes "
+                            "+ sync aggregate; wall time of SignatureSet.verify() (Python packing + H2D + kernels + D2H)"}
+        for mode, kw in (("strict", {}), ("registry", {"registry": reg_b})):
+            ts, dev = [], []
+            for i in range(7):
+                flush_l2()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                got = sset.verify(**kw)
+                dt = (time.perf_counter() - t0) * 1e3
+                assert got.tolist() == want, f"block signature set ({mode}) differs from the constructed expectation"
+                if i >= 2:
+                    ts.append(dt); dev.append(crypto.last_kernel_ms())
+            blockset[f"ms_per_block_{mode}"] = sorted(ts)[len(ts) // 2]
+            blockset[f"ms_last_call_device_{mode}"] = sorted(dev)[len(dev) // 2]
+        assert sset.first_failure(got) is None
+
     line = dict(base)
     peaks = {}
     if rank == 0:
@@ -477,7 +505,7 @@ def main():
                                        f"{(sample / cpu_dt) * cpu_1t:.1f}x (plain-C restatement of the reference semantics with a dedicated "
                                        "squaring; no assembly: blst is ~1.5-2x faster per core)"},
             "registry_mode": {"ms_per_step": reg_ms, "tuples_per_s": (T / (reg_ms / 1e3)) if reg_ms else None, "registry_load_ms": reg_load_ms},
-            "single_call_latency": single, "rlc_batch_all": rlc,
+            "single_call_latency": single, "rlc_batch_all": rlc, "block_signature_set": blockset,
             "wall_s_timed_region": t_all,
         })
     if strong is not None:

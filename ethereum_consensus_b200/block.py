@@ -146,7 +146,8 @@ class SignatureSet:
             return np.zeros(0, dtype=np.int32)
         codes = np.zeros(t, dtype=np.int32)
         by_index = [i for i, e in enumerate(self.entries) if registry is not None and e.indices is not None]
-        strict = [i for i in range(t) if i not in set(by_index)]
+        named = set(by_index)
+        strict = [i for i in range(t) if i not in named]
         if strict:
             ent = [self.entries[i] for i in strict]
             pks = np.frombuffer(b"".join(p for e in ent for p in e.pubkeys) or b"", dtype=np.uint8)

@@ -264,6 +264,17 @@ def fp_selftest(n: int = 1 << 16, seed: int = 1) -> int:
     return int(m.value)
 
 
+def tune(knob: str, value: int) -> None:
+    """Launch-shape knobs of the batch pipeline (include/b200_consensus.h, b200_tune): never change a result."""
+    _lib.check(_lib.lib().b200_tune(knob.encode(), int(value)), f"tune({knob})")
+
+
+def vm_load_programs(blob) -> None:
+    """Swap in another schedule of the pairing programs (uint32 words written by tools/gen_pairing_vm.py --blob)."""
+    a = np.ascontiguousarray(blob, dtype=np.uint32)
+    _lib.check(_lib.lib().b200_vm_load_programs(_lib.ptr(a), a.size), "vm_load_programs")
+
+
 def measure_int_peak(kind: int) -> float:
     """1e9 ops/s of IMAD.WIDE.U32 (0), IMAD.U32 (1) or the LOP3/SHF/IADD3 mix (2) measured on this device."""
     g = C.c_double(0)

@@ -175,6 +175,30 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
     if (!fp_eq(ab, r)) bad++;
     fp_mul_portable(r, a, a); fp_sqr(l, a);
     if (!fp_eq(l, r)) bad++;
+    {   // carry-chain add / subtract (fp.cuh) vs the portable 64-bit emulation, incl. equal operands, zero and p - 1
+        Fp x = a, y = b;
+        if ((i & 15) == 3) y = a;
+        if ((i & 15) == 5) x = fp_zero();
+        if ((i & 15) == 7) { y = fp_zero(); }
+        Fp u, v;
+        const uint32_t cu = fp_add_raw(u, x, y), cv = fp_add_raw_portable(v, x, y);
+        if (cu != cv || !fp_eq(u, v)) bad++;
+        const uint32_t bu = fp_sub_raw(u, x, y), bv = fp_sub_raw_portable(v, x, y);
+        if (bu != bv || !fp_eq(u, v)) bad++;
+        // field-level: (x + y) - y == x, x - y == -(y - x), 2x == x + x, x + (-x) == 0
+        fp_add(u, x, y); fp_sub(u, u, y);
+        if (!fp_eq(u, x)) bad++;
+        fp_sub(u, x, y); fp_sub(v, y, x); fp_neg(v, v);
+        if (!fp_eq(u, v)) bad++;
+        fp_dbl(u, x); fp_add(v, x, x);
+        if (!fp_eq(u, v)) bad++;
+        fp_neg(u, x); fp_add(u, u, x);
+        if (!fp_is_zero(u)) bad++;
+        fp_add_masked_raw(u, x, y, 0u);
+        if (!fp_eq(u, x)) bad++;
+        fp_add_masked_raw(u, x, y, 0xffffffffu); fp_add_raw_portable(v, x, y);
+        if (!fp_eq(u, v)) bad++;
+    }
     if ((i & 63) == 0 && !fp_is_zero(a)) {
         fp_inv(t, a); fp_mul(t, t, a);
         if (!fp_eq(t, fp_one())) bad++;
@@ -206,7 +230,7 @@ static int g_g1_variant = 7;
 static uint32_t g_g1_small_n = 3u * 148u * 384u;   // B200_G1_SMALL_N overrides (0: always 384-thread CTAs)
 void set_g1_small_n(uint32_t n) { g_g1_small_n = n; }
 void set_g1_variant(int v) { if (v >= 0 && v <= 7) g_g1_variant = v; }
-void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream) {
+void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream, int cta) {
     if (!n) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (g_g1_variant) {
@@ -215,7 +239,7 @@ void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* co
     default:
         // 12 warps per SM either way; below ~3 full waves of 384-thread CTAs the same kernel goes out as three 128-thread
         // CTAs per SM, so that the last, partial wave spreads over all SMs instead of leaving most of them idle
-        if (n <= g_g1_small_n)
+        if (cta == 128 || (cta != 384 && n <= g_g1_small_n))
             k_g1_validate_r168<<<(n + 127) / 128, 128, with_pow_tab(k_g1_validate_r168, 128), st>>>(keys, n, out, codes);
         else
             k_g1_validate_r168<<<(n + 383) / 384, 384, with_pow_tab(k_g1_validate_r168, 384), st>>>(keys, n, out, codes);

@@ -24,7 +24,10 @@ enum : int32_t { SIG_OK = 0, SIG_NOT_IN_GROUP = -1 };  // >0: blst decode error 
 void set_g1_variant(int v);
 void set_g1_small_n(uint32_t n);
 void set_small_cta(int threads);
-void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream);
+void set_vm_team16_max(uint32_t n);
+void set_vm_cta(int threads);
+// cta = 0: by batch size (384-thread CTAs above the small-batch bound, 128 below); 128 / 384 force one (default variant only)
+void launch_g1_validate(const uint8_t* keys, uint32_t n, G1Aff* out, int32_t* codes, void* stream, int cta = 0);
 // K2: per tuple t, sum the validated keys [off[t], off[t+1]) (or gather through `index` when non-null);
 //     first failing key (in order) decides pk_code[t]
 //     agg == nullptr: only the code scan (aggregate_verify keeps keys separate); extra_flags is OR-ed into flags
@@ -53,6 +56,8 @@ void launch_final(const Fp12* f, const uint32_t* pair_off, const int32_t* pk_cod
                   const int32_t* sig_code, uint32_t n_tuples, int32_t* out_codes, void* stream);
 // lane-parallel (team) versions of K5 / K6 for tuples with exactly two pairs (bls_vm.cu); vm_init returns 0 on success
 int vm_init(void* stream);
+// replaces one team size's scheduled programs (blob layout: bls_vm.cu); returns 0 on success, 1 on a malformed blob
+int vm_load_programs(const uint32_t* blob, size_t n_words, void* stream);
 void launch_vm_miller(const G1Pre* g1, const uint32_t* g1_idx, const G2Aff* g2, const uint32_t* g2_idx,
                       const uint32_t* pair_tuple, const int32_t* pk_code, const uint32_t* flags, const int32_t* sig_code,
                       uint32_t n_pairs, Fp12* f, void* stream);

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "bls_kernels.cuh"
@@ -23,6 +24,19 @@ namespace b200 {
 
 struct BlsState {
     cudaStream_t sb = nullptr, sc = nullptr;  // signatures / messages: run under the per-key kernel
+    // Chunked strict batches (OFF by default): the per-key kernel goes out in `chunks` key ranges on the engine stream, and
+    // each range's aggregate -> Miller loops -> final exponentiation chain runs on `sd` UNDER the next range's per-key
+    // kernel (B200_BLS_CHUNKS, 1 = one range; B200_BLS_CHUNK_MIN_TUPLES; B200_BLS_CHUNK_K1_CTA = 128 | 384).
+    // Measured on B200, T = 4096 x K = 512 (profiles/r2_ab_variants.txt, call 15): one range 130.2 ms; 2 ranges 137.3;
+    // 4 ranges 144.4 (138.8 with 384-thread K1 CTAs); 8 ranges 158.1.  The pairing chain does not fit under the per-key
+    // kernel: its CTAs need the registers / shared memory of a retiring per-key CTA, both kernels then run at reduced
+    // occupancy, and the per-key kernel loses more (114 -> 129 ms) than the 14 ms chain it hides.
+    static constexpr uint32_t kMaxChunks = 16;
+    cudaStream_t sd = nullptr, se = nullptr;   // se: odd key ranges, so that range c+1's CTAs fill range c's draining tail
+    cudaEvent_t ev_ck[kMaxChunks] = {nullptr}, ev_join = nullptr;
+    uint32_t chunks = 1, chunk_min_tuples = 2048;
+    int chunk_k1_cta = 128;
+    bool chunk_alt = true;
     cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp, gath;
     // RLC whole-batch check (bls_rlc.cu): Jacobian aggregates, scaled points, reduction ping-pong, zeros, indices, exchange
@@ -62,6 +76,16 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         if (const char* v = getenv("B200_SMALL_STREAM_PRIORITY")) prio = atoi(v);  // A/B knob
         B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sb, cudaStreamNonBlocking, prio));
         B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sc, cudaStreamNonBlocking, prio));
+        if (const char* v = getenv("B200_BLS_CHUNKS")) s->chunks = uint32_t(std::max(1, atoi(v)));
+        if (const char* v = getenv("B200_BLS_CHUNK_MIN_TUPLES")) s->chunk_min_tuples = uint32_t(std::max(2, atoi(v)));
+        if (const char* v = getenv("B200_BLS_CHUNK_K1_CTA")) s->chunk_k1_cta = atoi(v);
+        if (const char* v = getenv("B200_BLS_CHUNK_ALT")) s->chunk_alt = atoi(v) != 0;
+        int prio_d = prio;
+        if (const char* v = getenv("B200_PAIR_STREAM_PRIORITY")) prio_d = atoi(v);
+        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sd, cudaStreamNonBlocking, prio_d));
+        B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->se, cudaStreamNonBlocking, prio_lo));
+        for (auto& ev : s->ev_ck) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_c, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
         B200_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
@@ -124,6 +148,8 @@ static int32_t run_verify(Engine& e, BlsState& s, PairMode mode, const uint8_t* 
         cudaStreamSynchronize(e.stream);
         cudaStreamSynchronize(s.sb);
         cudaStreamSynchronize(s.sc);
+        cudaStreamSynchronize(s.sd);
+        cudaStreamSynchronize(s.se);
         cudaGetLastError();
     }
     return rc;
@@ -244,46 +270,102 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     }
     // ---- stream A: public keys
     B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
-    if (have_k1) {
-        launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, static_cast<G1Aff*>(s.key_aff.p),
-                           static_cast<int32_t*>(s.key_code.p), sa);
-        e.launches++;
-    }
-    if (!(have_k1 && s.small_order == 1)) {
-        if (have_k1 && s.small_order == 2) {  // strictly after the per-key kernel
-            B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
-        }
-        int32_t rc = launch_small();
-        if (rc) return rc;
-    }
-    B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
-    if (s.trace) cudaEventRecord(s.ev_t[0], sa);
-    const uint32_t n_agg_tuples = (mode == MODE_FAST_AGGREGATE) ? T : 1;
-    launch_g1_aggregate(key_aff, key_code, registry ? d_small + o_index : nullptr, d_small + o_koff, n_agg_tuples,
-                        (mode == MODE_FAST_AGGREGATE && !s.use_vm) ? d_g1 : nullptr,
-                        (mode == MODE_FAST_AGGREGATE && s.use_vm) ? static_cast<G1Pre*>(s.g1pre.p) : nullptr,
-                        static_cast<int32_t*>(s.pk_code.p), static_cast<uint32_t*>(s.flags.p),
-                        force_fail_shape ? uint32_t(TUPLE_FLAG_EMPTY) : 0u, sa,
-                        rlc ? static_cast<G1Jac*>(s.rlc_jac.p) : nullptr);
-    e.launches++;
+    const uint32_t n_chunks = (mode == MODE_FAST_AGGREGATE && !rlc && s.use_vm && have_k1 && s.small_order == 0 && !force_fail_shape &&
+                               s.chunks > 1 && T >= s.chunk_min_tuples) ? std::min(s.chunks, BlsState::kMaxChunks) : 1u;
+    const uint32_t* d_g1i = nullptr; const uint32_t* d_g2i = nullptr; const uint32_t* d_ptu = nullptr; const uint32_t* d_poff = nullptr;
+    bool chunked = false;
     const G1Aff* pair_g1 = d_g1;
-    if (mode == MODE_FAST_AGGREGATE) {
-        B200_CUDA_TRY(cudaMemcpyAsync(d_g1 + T, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
-        B200_CUDA_TRY(cudaMemcpyAsync(static_cast<G1Pre*>(s.g1pre.p) + T, s.d_negg1_pre, sizeof(G1Pre), cudaMemcpyDeviceToDevice, sa));
-    } else {
-        G1Aff* ka = static_cast<G1Aff*>(s.key_aff.p);
-        B200_CUDA_TRY(cudaMemcpyAsync(ka + n_keys, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
-        pair_g1 = ka;  // len(msgs) != len(pks) or no keys: flagged EMPTY above -> VERIFY_FAIL after the decoding checks
+    if (n_chunks > 1) {
+        // Chunked strict batch: tuple range c's keys are validated on stream A while range c-1's aggregate -> Miller ->
+        // final-exponentiation chain (latency-bound: ~1/3 of the IMAD pipe when alone) runs on stream D in the slots the
+        // per-key kernel's retiring 128-thread CTAs leave.  Same kernels, same per-tuple arithmetic, same code vector.
+        chunked = true;
+        cudaStream_t sd = s.sd;
+        d_g1i = d_small + o_g1i; d_g2i = d_g1i + n_pairs; d_ptu = d_g2i + n_pairs; d_poff = d_ptu + n_pairs;
+        uint32_t tb[BlsState::kMaxChunks + 1];
+        for (uint32_t c = 0; c <= n_chunks; c++) tb[c] = uint32_t(uint64_t(T) * c / n_chunks);
+        B200_CUDA_TRY(cudaStreamWaitEvent(s.se, s.ev_k0, 0));   // the key bytes
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const uint32_t k0 = key_off[tb[c]], k1 = key_off[tb[c + 1]];
+            cudaStream_t sk = ((c & 1u) && s.chunk_alt) ? s.se : sa;
+            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p) + size_t(k0) * 48, k1 - k0, static_cast<G1Aff*>(s.key_aff.p) + k0,
+                               static_cast<int32_t*>(s.key_code.p) + k0, sk, s.chunk_k1_cta);
+            if (k1 > k0) e.launches++;
+            B200_CUDA_TRY(cudaEventRecord(s.ev_ck[c], sk));
+            if (c == 0) {   // signature / message kernels right behind the first range, as in the one-range flow
+                int32_t rc = launch_small();
+                if (rc) return rc;
+            }
+        }
+        if (s.chunk_alt)
+            for (uint32_t c = 1; c < n_chunks; c += 2) B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_ck[c], 0));
+        B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
+        B200_CUDA_TRY(cudaStreamWaitEvent(sd, s.ev_in, 0));   // the small index arrays
+        B200_CUDA_TRY(cudaStreamWaitEvent(sd, s.ev_b, 0));
+        B200_CUDA_TRY(cudaStreamWaitEvent(sd, s.ev_c, 0));
+        B200_CUDA_TRY(cudaMemcpyAsync(static_cast<G1Pre*>(s.g1pre.p) + T, s.d_negg1_pre, sizeof(G1Pre), cudaMemcpyDeviceToDevice, sd));
+        int32_t* d_pk = static_cast<int32_t*>(s.pk_code.p);
+        uint32_t* d_fl = static_cast<uint32_t*>(s.flags.p);
+        const int32_t* d_sc = static_cast<const int32_t*>(s.sig_code.p);
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const uint32_t t0 = tb[c], nt = tb[c + 1] - tb[c];
+            if (!nt) continue;
+            B200_CUDA_TRY(cudaStreamWaitEvent(sd, s.ev_ck[c], 0));
+            launch_g1_aggregate(key_aff, key_code, nullptr, d_small + o_koff + t0, nt, nullptr, static_cast<G1Pre*>(s.g1pre.p) + t0,
+                                d_pk + t0, d_fl + t0, 0u, sd, nullptr);
+            // pair-indexed arrays start at 2 t0 (values are absolute); tuple-indexed code arrays are read through pair_tuple
+            launch_vm_miller(static_cast<const G1Pre*>(s.g1pre.p), d_g1i + 2 * t0, d_g2, d_g2i + 2 * t0, d_ptu + 2 * t0, d_pk, d_fl, d_sc,
+                             2 * nt, static_cast<Fp12*>(s.f.p) + 2 * size_t(t0), sd);
+            // f BASE + absolute pair offsets; tuple-indexed arrays start at t0
+            launch_vm_final(static_cast<const Fp12*>(s.f.p), d_poff + t0, d_pk + t0, d_fl + t0, d_sc + t0, nt,
+                            static_cast<int32_t*>(s.out.p) + t0, sd);
+            e.launches += 3;
+        }
+        B200_CUDA_TRY(cudaEventRecord(s.ev_join, sd));
+        B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_join, 0));
+        if (s.trace) { cudaEventRecord(s.ev_t[0], sa); cudaEventRecord(s.ev_t[1], sa); cudaEventRecord(s.ev_t[2], sa); cudaEventRecord(s.ev_t[3], sa); }
     }
-    // ---- join, pairing
-    if (s.trace) cudaEventRecord(s.ev_t[1], sa);
-    B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_b, 0));
-    B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_c, 0));
-    if (s.trace) cudaEventRecord(s.ev_t[2], sa);
-    const uint32_t* d_g1i = d_small + o_g1i;
-    const uint32_t* d_g2i = d_g1i + n_pairs;
-    const uint32_t* d_ptu = d_g2i + n_pairs;
-    const uint32_t* d_poff = d_ptu + n_pairs;
+    if (!chunked) {
+        if (have_k1) {
+            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, static_cast<G1Aff*>(s.key_aff.p),
+                               static_cast<int32_t*>(s.key_code.p), sa);
+            e.launches++;
+        }
+        if (!(have_k1 && s.small_order == 1)) {
+            if (have_k1 && s.small_order == 2) {  // strictly after the per-key kernel
+                B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
+            }
+            int32_t rc = launch_small();
+            if (rc) return rc;
+        }
+        B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
+        if (s.trace) cudaEventRecord(s.ev_t[0], sa);
+        const uint32_t n_agg_tuples = (mode == MODE_FAST_AGGREGATE) ? T : 1;
+        launch_g1_aggregate(key_aff, key_code, registry ? d_small + o_index : nullptr, d_small + o_koff, n_agg_tuples,
+                            (mode == MODE_FAST_AGGREGATE && !s.use_vm) ? d_g1 : nullptr,
+                            (mode == MODE_FAST_AGGREGATE && s.use_vm) ? static_cast<G1Pre*>(s.g1pre.p) : nullptr,
+                            static_cast<int32_t*>(s.pk_code.p), static_cast<uint32_t*>(s.flags.p),
+                            force_fail_shape ? uint32_t(TUPLE_FLAG_EMPTY) : 0u, sa,
+                            rlc ? static_cast<G1Jac*>(s.rlc_jac.p) : nullptr);
+        e.launches++;
+        if (mode == MODE_FAST_AGGREGATE) {
+            B200_CUDA_TRY(cudaMemcpyAsync(d_g1 + T, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
+            B200_CUDA_TRY(cudaMemcpyAsync(static_cast<G1Pre*>(s.g1pre.p) + T, s.d_negg1_pre, sizeof(G1Pre), cudaMemcpyDeviceToDevice, sa));
+        } else {
+            G1Aff* ka = static_cast<G1Aff*>(s.key_aff.p);
+            B200_CUDA_TRY(cudaMemcpyAsync(ka + n_keys, s.d_negg1, sizeof(G1Aff), cudaMemcpyDeviceToDevice, sa));
+            pair_g1 = ka;  // len(msgs) != len(pks) or no keys: flagged EMPTY above -> VERIFY_FAIL after the decoding checks
+        }
+        // ---- join, pairing
+        if (s.trace) cudaEventRecord(s.ev_t[1], sa);
+        B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_b, 0));
+        B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_c, 0));
+        if (s.trace) cudaEventRecord(s.ev_t[2], sa);
+    }
+    d_g1i = d_small + o_g1i;
+    d_g2i = d_g1i + n_pairs;
+    d_ptu = d_g2i + n_pairs;
+    d_poff = d_ptu + n_pairs;
     if (rlc) {
         // ---- RLC whole-batch check (bls_rlc.cu): T Miller loops + ONE final exponentiation
         const size_t kPart = kRlcPart;
@@ -384,7 +466,9 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
         }
         return B200_SUCCESS;
     }
-    if (mode == MODE_FAST_AGGREGATE && s.use_vm) {
+    if (chunked) {
+        // every range's Miller loops and final exponentiations are already queued on stream D (joined above)
+    } else if (mode == MODE_FAST_AGGREGATE && s.use_vm) {
         launch_vm_miller(static_cast<const G1Pre*>(s.g1pre.p), d_g1i, d_g2, d_g2i, d_ptu, static_cast<const int32_t*>(s.pk_code.p),
                          static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), n_pairs,
                          static_cast<Fp12*>(s.f.p), sa);
@@ -400,13 +484,14 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
                      static_cast<const uint32_t*>(s.flags.p), static_cast<const int32_t*>(s.sig_code.p), T,
                      static_cast<int32_t*>(s.out.p), sa);
     }
-    e.launches += (n_pairs ? 1 : 0) + (T ? 1 : 0);
+    if (!chunked) e.launches += (n_pairs ? 1 : 0) + (T ? 1 : 0);
     B200_CUDA_TRY(cudaEventRecord(s.ev_k1, sa));
     B200_CUDA_TRY(cudaGetLastError());
     B200_CUDA_TRY(cudaMemcpyAsync(h_out + 4, s.out.p, size_t(T) * 4, cudaMemcpyDeviceToHost, sa));
     B200_CUDA_TRY(cudaStreamSynchronize(sa));
     B200_CUDA_TRY(cudaStreamSynchronize(sb));
     B200_CUDA_TRY(cudaStreamSynchronize(sc));
+    if (chunked) B200_CUDA_TRY(cudaStreamSynchronize(s.sd));
     B200_CUDA_TRY(cudaEventElapsedTime(&e.last_kernel_ms, s.ev_k0, s.ev_k1));
     B200_CUDA_TRY(cudaEventElapsedTime(&s.last_dominant_ms, s.ev_d0, s.ev_d1));
     if (s.trace) {
@@ -426,6 +511,39 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
 using namespace b200;
 
 extern "C" {
+
+int32_t b200_tune(const char* knob, int64_t value) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    if (!knob) return B200_ERR_BAD_ARG;
+    const std::string k(knob);
+    if (k == "bls_chunks") s->chunks = uint32_t(std::max<int64_t>(1, value));
+    else if (k == "bls_chunk_min_tuples") s->chunk_min_tuples = uint32_t(std::max<int64_t>(2, value));
+    else if (k == "bls_chunk_k1_cta") s->chunk_k1_cta = int(value);
+    else if (k == "bls_chunk_alt") s->chunk_alt = value != 0;
+    else if (k == "vm_team16_max") set_vm_team16_max(uint32_t(std::max<int64_t>(0, value)));
+    else if (k == "vm_cta") set_vm_cta(int(value));
+    else return B200_ERR_BAD_ARG;
+    return B200_SUCCESS;
+}
+
+int32_t b200_vm_load_programs(const uint32_t* blob, size_t n_words) {
+    Engine& e = engine();
+    Guard g(e);
+    int32_t rc = check_ready(e);
+    if (rc) return rc;
+    BlsState* s;
+    rc = bls_state(e, &s);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    if (vm_load_programs(blob, n_words, e.stream) != 0) { e.last_error = "malformed pairing-VM program blob"; return B200_ERR_BAD_ARG; }
+    return B200_SUCCESS;
+}
 
 float b200_last_dominant_kernel_ms(void) {
     Engine& e = engine();

@@ -61,8 +61,12 @@ B200_HD bool fp_geq_raw(const Fp& a, const Fp& b) {
     }
     return borrow == 0;
 }
-// r = a - b (mod 2^384), returns the borrow
-B200_HD uint32_t fp_sub_raw(Fp& r, const Fp& a, const Fp& b) {
+// Raw 384-bit add / subtract.  On the device: hardware carry chains (add.cc / addc.cc -> one IADD3.X per limb); the
+// portable 64-bit emulation below compiles to THREE dependent instructions per limb (IADD3 + IADD3.X + LOP3, several of them
+// IMAD.X / IMAD.IADD on the FMA pipe the products need), which made a plain Fp2 addition ~150 SASS instructions in the
+// pairing VM's light rounds.  -DB200_FP_ADD_PORTABLE restores the emulation on the device (A/B).  Outputs may alias inputs:
+// asm operands are distinct PTX virtual registers.
+B200_HD uint32_t fp_sub_raw_portable(Fp& r, const Fp& a, const Fp& b) {
     uint64_t borrow = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -72,7 +76,7 @@ B200_HD uint32_t fp_sub_raw(Fp& r, const Fp& a, const Fp& b) {
     }
     return uint32_t(borrow);
 }
-B200_HD uint32_t fp_add_raw(Fp& r, const Fp& a, const Fp& b) {
+B200_HD uint32_t fp_add_raw_portable(Fp& r, const Fp& a, const Fp& b) {
     uint64_t carry = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -82,12 +86,101 @@ B200_HD uint32_t fp_add_raw(Fp& r, const Fp& a, const Fp& b) {
     }
     return uint32_t(carry);
 }
+#if defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE) && !defined(B200_FP_ADD_PORTABLE)
+#define B200_FP_ADD_PTX 1
+// r = a - b (mod 2^384), returns the borrow (0 / 1)
+__device__ __forceinline__ uint32_t fp_sub_raw(Fp& r, const Fp& a, const Fp& b) {
+    uint32_t c;
+    asm("sub.cc.u32 %0, %13, %25;\n\t"
+        "subc.cc.u32 %1, %14, %26;\n\t"
+        "subc.cc.u32 %2, %15, %27;\n\t"
+        "subc.cc.u32 %3, %16, %28;\n\t"
+        "subc.cc.u32 %4, %17, %29;\n\t"
+        "subc.cc.u32 %5, %18, %30;\n\t"
+        "subc.cc.u32 %6, %19, %31;\n\t"
+        "subc.cc.u32 %7, %20, %32;\n\t"
+        "subc.cc.u32 %8, %21, %33;\n\t"
+        "subc.cc.u32 %9, %22, %34;\n\t"
+        "subc.cc.u32 %10, %23, %35;\n\t"
+        "subc.cc.u32 %11, %24, %36;\n\t"
+        "subc.u32 %12, 0, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11]), "=r"(c)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]), "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+    return c & 1u;   // 0 - 0 - borrow
+}
+// r = a + b (mod 2^384), returns the carry
+__device__ __forceinline__ uint32_t fp_add_raw(Fp& r, const Fp& a, const Fp& b) {
+    uint32_t c;
+    asm("add.cc.u32 %0, %13, %25;\n\t"
+        "addc.cc.u32 %1, %14, %26;\n\t"
+        "addc.cc.u32 %2, %15, %27;\n\t"
+        "addc.cc.u32 %3, %16, %28;\n\t"
+        "addc.cc.u32 %4, %17, %29;\n\t"
+        "addc.cc.u32 %5, %18, %30;\n\t"
+        "addc.cc.u32 %6, %19, %31;\n\t"
+        "addc.cc.u32 %7, %20, %32;\n\t"
+        "addc.cc.u32 %8, %21, %33;\n\t"
+        "addc.cc.u32 %9, %22, %34;\n\t"
+        "addc.cc.u32 %10, %23, %35;\n\t"
+        "addc.cc.u32 %11, %24, %36;\n\t"
+        "addc.u32 %12, 0, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11]), "=r"(c)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]), "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+    return c;
+}
+// r = a + (m & mask) (mod 2^384), mask = 0 or 0xffffffff: the branch-free "add the modulus back after a borrow"
+__device__ __forceinline__ void fp_add_masked_raw(Fp& r, const Fp& a, const Fp& m, uint32_t mask) {
+    asm("{\n\t"
+        ".reg .u32 m<12>;\n\t"
+        "and.b32 m0, %24, %36;\n\t"
+        "and.b32 m1, %25, %36;\n\t"
+        "and.b32 m2, %26, %36;\n\t"
+        "and.b32 m3, %27, %36;\n\t"
+        "and.b32 m4, %28, %36;\n\t"
+        "and.b32 m5, %29, %36;\n\t"
+        "and.b32 m6, %30, %36;\n\t"
+        "and.b32 m7, %31, %36;\n\t"
+        "and.b32 m8, %32, %36;\n\t"
+        "and.b32 m9, %33, %36;\n\t"
+        "and.b32 m10, %34, %36;\n\t"
+        "and.b32 m11, %35, %36;\n\t"
+        "add.cc.u32 %0, %12, m0;\n\t"
+        "addc.cc.u32 %1, %13, m1;\n\t"
+        "addc.cc.u32 %2, %14, m2;\n\t"
+        "addc.cc.u32 %3, %15, m3;\n\t"
+        "addc.cc.u32 %4, %16, m4;\n\t"
+        "addc.cc.u32 %5, %17, m5;\n\t"
+        "addc.cc.u32 %6, %18, m6;\n\t"
+        "addc.cc.u32 %7, %19, m7;\n\t"
+        "addc.cc.u32 %8, %20, m8;\n\t"
+        "addc.cc.u32 %9, %21, m9;\n\t"
+        "addc.cc.u32 %10, %22, m10;\n\t"
+        "addc.u32 %11, %23, m11;\n\t"
+        "}"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]), "r"(m.l[0]), "r"(m.l[1]), "r"(m.l[2]), "r"(m.l[3]), "r"(m.l[4]), "r"(m.l[5]), "r"(m.l[6]), "r"(m.l[7]), "r"(m.l[8]), "r"(m.l[9]), "r"(m.l[10]), "r"(m.l[11]), "r"(mask));
+}
+#else
+B200_HD uint32_t fp_sub_raw(Fp& r, const Fp& a, const Fp& b) { return fp_sub_raw_portable(r, a, b); }
+B200_HD uint32_t fp_add_raw(Fp& r, const Fp& a, const Fp& b) { return fp_add_raw_portable(r, a, b); }
+B200_HD void fp_add_masked_raw(Fp& r, const Fp& a, const Fp& m, uint32_t mask) {
+    Fp t;
+#pragma unroll
+    for (int i = 0; i < 12; i++) t.l[i] = m.l[i] & mask;
+    fp_add_raw_portable(r, a, t);
+}
+#endif
+// select without a branch: r = take_t ? t : r
+B200_HD void fp_select(Fp& r, const Fp& t, bool take_t) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = take_t ? t.l[i] : r.l[i];
+}
 // conditional final subtraction: r in [0, 2p) -> [0, p)
 B200_HD void fp_reduce_once(Fp& r) {
     const Fp p = fp_p();
     Fp t;
     uint32_t borrow = fp_sub_raw(t, r, p);
-    if (!borrow) r = t;
+    fp_select(r, t, borrow == 0);
 }
 B200_HD void fp_add(Fp& r, const Fp& a, const Fp& b) {
     fp_add_raw(r, a, b);  // p < 2^381: no carry out of 384 bits
@@ -97,13 +190,15 @@ B200_HD void fp_sub(Fp& r, const Fp& a, const Fp& b) {
     const Fp p = fp_p();
     Fp t;
     uint32_t borrow = fp_sub_raw(t, a, b);
-    if (borrow) fp_add_raw(t, t, p);
-    r = t;
+    fp_add_masked_raw(r, t, p, 0u - borrow);
 }
-B200_HD void fp_neg(Fp& r, const Fp& a) {
-    if (fp_is_zero(a)) { r = a; return; }
+B200_HD void fp_neg(Fp& r, const Fp& a) {   // 0 -> 0, otherwise p - a; no branch
     const Fp p = fp_p();
-    fp_sub_raw(r, p, a);
+    const uint32_t nz = fp_is_zero(a) ? 0u : 0xffffffffu;
+    Fp t;
+    fp_sub_raw(t, p, a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = t.l[i] & nz;
 }
 B200_HD void fp_dbl(Fp& r, const Fp& a) { fp_add(r, a, a); }
 

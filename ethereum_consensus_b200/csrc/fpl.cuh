@@ -26,7 +26,7 @@ B200_HD void fpl_reduce_2p(Fp& r) {
     const Fp pp = fp_2p();
     Fp t;
     const uint32_t borrow = fp_sub_raw(t, r, pp);
-    if (!borrow) r = t;
+    fp_select(r, t, borrow == 0);
 }
 B200_HD FpL fpl_from_fp(const Fp& a) { FpL r; r.v = a; return r; }
 // canonical representative in [0, p)
@@ -39,8 +39,7 @@ B200_HD void f_add(FpL& r, const FpL& a, const FpL& b) {
 B200_HD void f_sub(FpL& r, const FpL& a, const FpL& b) {
     Fp t;
     const uint32_t borrow = fp_sub_raw(t, a.v, b.v);
-    if (borrow) { const Fp pp = fp_2p(); fp_add_raw(t, t, pp); }
-    r.v = t;
+    fp_add_masked_raw(r.v, t, fp_2p(), 0u - borrow);
 }
 B200_HD void f_dbl(FpL& r, const FpL& a) { f_add(r, a, a); }
 B200_HD void f_neg(FpL& r, const FpL& a) {

@@ -25,6 +25,8 @@ struct VmRfDense {
 #define B200_VM_SLOT_WORDS 28
 #endif
 constexpr int kVmSlotWords = B200_VM_SLOT_WORDS;
+constexpr int kVmMaxSmemBytes = 227 * 1024;          // opt-in dynamic shared memory per CTA on sm_100
+constexpr uint32_t kVmBlobMagic = 0xB200564Du;       // run-time program blobs (vm_load_programs)
 struct VmRfStrided {
     uint32_t* p;
     B200_HD Fp2 load(uint32_t i) const {

@@ -233,6 +233,17 @@ B200_API float b200_last_dominant_kernel_ms(void);
 /* Measured integer-pipe peak on this device, 1e9 ops/s: kind 0 IMAD.WIDE.U32 (Montgomery multiply-add), 1 IMAD.U32,
  * 2 LOP3/SHF/IADD3 mix (SHA-256 round ops).  Roofline denominators for bench.py. */
 B200_API int32_t b200_measure_int_peak(int32_t kind, double* gops);
+/* Scheduling knobs of the BLS batch pipeline, settable at run time (the same names, upper-cased with a B200_ prefix, are
+ * read from the environment when the pipeline is first used).  They change launch shapes only, never a result:
+ *   "bls_chunks" (key ranges per strict batch, 1 = off), "bls_chunk_min_tuples", "bls_chunk_k1_cta" (128 | 384),
+ *   "bls_chunk_alt" (0 | 1: alternate key ranges over two streams), "vm_team16_max", "vm_cta" (32 | 64 | 128).
+ * Unknown knob -> B200_ERR_BAD_ARG. */
+B200_API int32_t b200_tune(const char* knob, int64_t value);
+/* Replaces the scheduled Miller-loop / final-exponentiation programs of one team size (8 or 16 lanes) of the lane-parallel
+ * pairing kernels with another SCHEDULE of the same formulas: `blob` is what `tools/gen_pairing_vm.py <team> ... --blob F`
+ * writes after executing the schedule numerically against the direct evaluation.  Opcodes and slot indices are validated;
+ * a malformed blob -> B200_ERR_BAD_ARG and the programs in use stay.  Schedule tuning only: results never depend on it. */
+B200_API int32_t b200_vm_load_programs(const uint32_t* blob, size_t n_words);
 /* On-device self-test of the field arithmetic over `n` pseudo-random triples; *mismatches must come back 0. */
 B200_API int32_t b200_fp_selftest(uint32_t n, uint32_t seed, uint32_t* mismatches);
 

@@ -108,30 +108,7 @@ def test_configs3_block_signature_set_spec_shape(engine, oracle_bls_c):
     orc = oracle_bls_c
     registry, rows = workloads.make_deneb_block_plan(orc, threads=_threads())
     assert len(rows) == 215
-    pk = registry                                   # validator_pubkeys[i] -> 48 bytes
-    getpk = lambda i: pk[i].tobytes()               # noqa: E731
-    fork = signing.Fork(bytes.fromhex("03000000"), bytes.fromhex("04000000"), 269568)
-    gvr = hashlib.sha256(b"gvr").digest()
-
-    class Keys:                                     # lazy `state.validators[i].public_key`
-        def __len__(self): return len(pk)
-        def __getitem__(self, i): return getpk(i)
-
-    s = block.SignatureSet()
-    for r in rows:
-        if r["site"] in ("attestation", "attester_slashing"):
-            s.add_indexed_attestation(r["site"], Keys(), r["indices"], r["root"], r["sig"])
-        elif r["site"] == "sync_aggregate":
-            # through the collector's own gather (altair/block_processing.rs:216-243); the row was signed over r["root"], so
-            # hand the pre-computed signing root in by entry surgery after checking the gather picked the same signers
-            s.add_sync_aggregate([getpk(i) for i in r["committee"]], r["bits"], r["sig"], 8_626_177, hashlib.sha256(b"prev").digest(), fork, gvr,
-                                 committee_indices=r["committee"])
-            assert s.entries[-1].indices == r["indices"]
-            s.entries[-1].signing_root = r["root"]
-        elif r["indices"] is not None:
-            s.add_by_index(r["site"], Keys(), r["indices"], r["root"], r["sig"])
-        else:
-            s.add(r["site"], r["pubkeys"], r["root"], r["sig"], tolerant=r["tolerant"], eth_variant=r["eth"])
+    s = workloads.collect_block_signature_set(registry, rows)
     strict = s.verify()
     assert strict.tolist() == [r["expect"] for r in rows]
 

@@ -135,3 +135,40 @@ def make_deneb_block_plan(orc, n_registry: int = 1 << 20, n_distinct: int = 1 <<
         rows[dep[3]]["sig"] = rows[dep[4]]["sig"]; rows[dep[3]]["expect"] = 5
         rows[dep[7]]["pubkeys"] = [bytes(48)]; rows[dep[7]]["expect"] = 1
     return registry, rows
+
+
+class LazyKeys:
+    """`state.validators[i].public_key` over the registry array, without materialising 2^20 bytes objects."""
+    def __init__(self, registry):
+        self.registry = registry
+
+    def __len__(self):
+        return len(self.registry)
+
+    def __getitem__(self, i):
+        return self.registry[i].tobytes()
+
+
+def collect_block_signature_set(registry, rows):
+    """Feeds a make_deneb_block_plan() plan through the host-side collector (ethereum_consensus_b200.block.SignatureSet)
+    in execution order, the way process_block's sites would."""
+    from ethereum_consensus_b200 import block, signing
+    keys = LazyKeys(registry)
+    fork = signing.Fork(bytes.fromhex("03000000"), bytes.fromhex("04000000"), 269568)
+    gvr = hashlib.sha256(b"gvr").digest()
+    s = block.SignatureSet()
+    for r in rows:
+        if r["site"] in ("attestation", "attester_slashing"):
+            s.add_indexed_attestation(r["site"], keys, r["indices"], r["root"], r["sig"])
+        elif r["site"] == "sync_aggregate":
+            # through the collector's own gather (altair/block_processing.rs:216-243); the row was signed over r["root"], so
+            # hand the pre-computed signing root in by entry surgery after checking the gather picked the same signers
+            s.add_sync_aggregate([keys[i] for i in r["committee"]], r["bits"], r["sig"], 8_626_177, hashlib.sha256(b"prev").digest(), fork, gvr,
+                                 committee_indices=r["committee"])
+            assert s.entries[-1].indices == r["indices"]
+            s.entries[-1].signing_root = r["root"]
+        elif r["indices"] is not None:
+            s.add_by_index(r["site"], keys, r["indices"], r["root"], r["sig"])
+        else:
+            s.add(r["site"], r["pubkeys"], r["root"], r["sig"], tolerant=r["tolerant"], eth_variant=r["eth"])
+    return s

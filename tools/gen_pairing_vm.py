@@ -22,6 +22,7 @@ from oracle import bls_oracle as bo  # noqa: E402  (generator-time checks only)
 P = bo.P
 Z_ABS = bo.Z_ABS
 
+HEAVY_MIN = 1       # with MIX_LIGHT: a heavy round needs this many ready ops of its class while light ops are also ready (--heavy-min)
 MIX_LIGHT = False  # True: ready light ops ride in the idle lanes of heavy rounds (measured offline: halves the rounds but doubles the rounds that pay for a product - a loss)
 
 # opcodes (must match pairing_vm.cuh)
@@ -353,10 +354,11 @@ def schedule(tr, outputs, team, window=None):
             cl = HEAVY.get(op, "light")
             classes.setdefault(cl, []).append(i)
         heavy_classes = [c for c in classes if c != "light"]
-        if MIX_LIGHT and heavy_classes:
-            # a heavy round whenever one is possible; lanes the heavy class leaves idle carry ready light ops (they
-            # diverge from the product code, but a light op is ~4 % of a product and would otherwise cost a round)
-            cl = max(heavy_classes, key=lambda c: max(prio[i] for i in classes[c]))
+        full_enough = [c for c in heavy_classes if len(classes[c]) >= min(HEAVY_MIN, team) or "light" not in classes]
+        if MIX_LIGHT and full_enough:
+            # a heavy round whenever one is possible (and full enough); lanes the heavy class leaves idle carry ready light
+            # ops (they diverge from the product code, but a light op is a few % of a product and would otherwise cost a round)
+            cl = max(full_enough, key=lambda c: max(prio[i] for i in classes[c]))
             pick = sorted(classes[cl], key=lambda i: -prio[i])[:team]
             if len(pick) < team and "light" in classes:
                 pick += sorted(classes["light"], key=lambda i: -prio[i])[:team - len(pick)]
@@ -538,7 +540,35 @@ def emit(team, miller, final):
     return path
 
 
+def write_blob(path, team, miller, final):
+    """Run-time loadable form of one team size's programs (b200_vm_load_programs; layout in csrc/bls_vm.cu)."""
+    import struct
+    (m_rounds, m_nslots, m_out), (f_rounds, f_nslots, f_out) = miller, final
+    def words(rounds):
+        out = []
+        for row in rounds:
+            ws = [(op | (d << 8) | (a << 16) | (b << 24)) for op, d, a, b in row]
+            out += ws + [NOP] * (team - len(ws))
+        return out
+    blob = [0xB200564D, team, len(m_rounds), m_nslots, *m_out, len(f_rounds), f_nslots, *f_out] + words(m_rounds) + words(f_rounds)
+    Path(path).write_bytes(struct.pack(f"<{len(blob)}I", *blob))
+    return path
+
+
 def main():
+    blob_path = None
+    if "--blob" in sys.argv:
+        i = sys.argv.index("--blob")
+        blob_path = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
+    global MIX_LIGHT, HEAVY_MIN
+    if "--mix-light" in sys.argv:
+        sys.argv.remove("--mix-light")
+        MIX_LIGHT = True
+    if "--heavy-min" in sys.argv:
+        i = sys.argv.index("--heavy-min")
+        HEAVY_MIN = int(sys.argv[i + 1])
+        del sys.argv[i:i + 2]
     team = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     # scheduling windows (Miller, final): measured trade-off between heavy rounds and register-file slots, see
     # profiles/r1_tuning.md; defaults: team 16 -> (256, 48), team 8 -> (96, 96).  BOTH headers ship: teams of 8 lanes have the
@@ -550,10 +580,19 @@ def main():
     for name, (rounds, nslots, _o) in (("miller", miller), ("final", final)):
         heavy = [r for r in rounds if r and any(o[0] in HEAVY for o in r)]
         util = sum(len(r) for r in heavy) / max(1, len(heavy) * team)
+        import collections
+        kinds = collections.Counter()
+        for r in rounds:
+            hv = sorted({HEAVY[o[0]] for o in r if o[0] in HEAVY})
+            lt = len({o[0] for o in r if o[0] not in HEAVY})
+            kinds[("+".join(hv) or "light") + (f"+{lt}L" if hv and lt else "")] += 1
         print(f"{name}: {len(rounds)} rounds ({len(heavy)} heavy, lane utilisation {util:.2f}), {nslots} slots, "
-              f"{sum(len(r) for r in rounds)} instructions")
+              f"{sum(len(r) for r in rounds)} instructions; round kinds {dict(kinds)}")
     selfcheck(team, miller, final)
-    print("self-check ok; wrote", emit(team, miller, final))
+    if blob_path:
+        print("self-check ok; wrote", write_blob(blob_path, team, miller, final))
+    else:
+        print("self-check ok; wrote", emit(team, miller, final))
 
 
 if __name__ == "__main__":
