@@ -138,30 +138,35 @@ class SignatureSet:
     # ---- one batch call for the whole block
     def verify(self, registry: Optional["crypto.Registry"] = None) -> np.ndarray:
         """int32 code per entry, exactly what the per-call reference functions would have returned.
-        With a `registry` (validated `state.validators` keys resident in HBM) the entries that name their signers by
-        validator index go through `…_batch_indexed`; entries whose key comes from the message itself (deposits,
-        bls-to-execution changes) always take the strict path.  Same codes either way."""
+        With a `registry` (validated `state.validators` keys resident in HBM) the whole set is ONE `…_batch_mixed` call:
+        entries that name their signers by validator index gather from the registry, keys that come with the message
+        itself (deposits, bls-to-execution changes) are validated in the same call.  Same codes either way."""
         t = len(self.entries)
         if t == 0:
             return np.zeros(0, dtype=np.int32)
-        codes = np.zeros(t, dtype=np.int32)
-        by_index = [i for i, e in enumerate(self.entries) if registry is not None and e.indices is not None]
-        named = set(by_index)
-        strict = [i for i in range(t) if i not in named]
-        if strict:
-            ent = [self.entries[i] for i in strict]
+        if registry is None:
+            ent = self.entries
             pks = np.frombuffer(b"".join(p for e in ent for p in e.pubkeys) or b"", dtype=np.uint8)
             off = np.cumsum([0] + [len(e.pubkeys) for e in ent]).astype(np.uint32)
             msgs = np.frombuffer(b"".join(e.signing_root for e in ent), dtype=np.uint8)
             sigs = np.frombuffer(b"".join(e.signature for e in ent), dtype=np.uint8)
-            codes[strict] = crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs)
-        if by_index:
-            ent = [self.entries[i] for i in by_index]
-            idx = np.array([j for e in ent for j in e.indices], dtype=np.uint32)
-            off = np.cumsum([0] + [len(e.indices) for e in ent]).astype(np.uint32)
-            msgs = np.frombuffer(b"".join(e.signing_root for e in ent), dtype=np.uint8)
-            sigs = np.frombuffer(b"".join(e.signature for e in ent), dtype=np.uint8)
-            codes[by_index] = registry.verify_batch(idx, off, msgs, sigs)
+            codes = crypto.fast_aggregate_verify_batch(pks, off, msgs, sigs).copy()
+        else:
+            # ONE call for the whole set: signers named by validator index gather from the resident registry; keys carried
+            # by the block (deposits, bls-to-execution changes) ride along as extra keys, validated in the same call
+            extra, idx = [], []
+            for e in self.entries:
+                if e.indices is not None:
+                    idx.extend(e.indices)
+                else:
+                    for p in e.pubkeys:
+                        idx.append(registry.n + len(extra))
+                        extra.append(p)
+            off = np.cumsum([0] + [len(e.indices) if e.indices is not None else len(e.pubkeys) for e in self.entries]).astype(np.uint32)
+            msgs = np.frombuffer(b"".join(e.signing_root for e in self.entries), dtype=np.uint8)
+            sigs = np.frombuffer(b"".join(e.signature for e in self.entries), dtype=np.uint8)
+            xk = np.frombuffer(b"".join(extra), dtype=np.uint8) if extra else None
+            codes = registry.verify_batch(np.array(idx, dtype=np.uint32), off, msgs, sigs, extra_keys=xk).copy()
         for i, e in enumerate(self.entries):  # eth_fast_aggregate_verify: no participants + infinity signature is Ok
             if e.eth_variant and not e.pubkeys and e.signature == crypto.INFINITY_COMPRESSED_SIGNATURE:
                 codes[i] = 0

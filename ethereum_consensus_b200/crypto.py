@@ -222,15 +222,23 @@ class Registry:
         _lib.check(_lib.lib().b200_registry_key_codes(_lib.ptr(out), self.n), "registry_key_codes")
         return out[:self.n]
 
-    def verify_batch(self, indices, offsets, msgs32, sigs) -> np.ndarray:
+    def verify_batch(self, indices, offsets, msgs32, sigs, extra_keys=None) -> np.ndarray:
+        """`extra_keys` (flat 48-byte keys): keys that arrive with the block (deposits, bls-to-execution changes); index
+        self.n + j names extra key j, which this call validates like the strict path would (`..._batch_mixed`)."""
         idx = np.ascontiguousarray(indices, dtype=np.uint32)
         off = np.ascontiguousarray(offsets, dtype=np.uint32)
         t = len(off) - 1
         if t < 0 or len(idx) != int(off[-1]) or _nbytes(msgs32) != 32 * t or _nbytes(sigs) != 96 * t:
             raise ValueError("indices / offsets / msgs / sigs sizes are inconsistent")
         out = np.empty(max(t, 1), dtype=np.int32)
-        _lib.check(_lib.lib().b200_fast_aggregate_verify_batch_indexed(_lib.ptr(idx), _lib.ptr(off), _lib.ptr(msgs32),
-                                                                       _lib.ptr(sigs), t, _lib.ptr(out)), "verify_batch_indexed")
+        if extra_keys is not None and _nbytes(extra_keys):
+            if _nbytes(extra_keys) % 48:
+                raise ValueError("extra keys must be 48 bytes each")
+            _lib.check(_lib.lib().b200_fast_aggregate_verify_batch_mixed(_lib.ptr(extra_keys), _nbytes(extra_keys) // 48, _lib.ptr(idx), _lib.ptr(off),
+                                                                         _lib.ptr(msgs32), _lib.ptr(sigs), t, _lib.ptr(out)), "verify_batch_mixed")
+        else:
+            _lib.check(_lib.lib().b200_fast_aggregate_verify_batch_indexed(_lib.ptr(idx), _lib.ptr(off), _lib.ptr(msgs32),
+                                                                           _lib.ptr(sigs), t, _lib.ptr(out)), "verify_batch_indexed")
         return out[:t]
 
 

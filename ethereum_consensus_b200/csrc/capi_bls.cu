@@ -121,6 +121,8 @@ static int32_t check_ready(Engine& e) {
 enum PairMode { MODE_FAST_AGGREGATE = 0, MODE_AGGREGATE = 1 };
 // message offsets travel as uint32 (32 bytes per tuple on the batch paths): 32 * T must not wrap
 constexpr size_t kMaxBatchTuples = size_t(1) << 26;
+// keys a `..._batch_mixed` call may bring along (a block carries <= 16 deposits + 16 bls-to-execution changes)
+constexpr size_t kRegistryExtraKeys = size_t(1) << 16;
 
 // Core: `n_tuples` tuples.  MODE_FAST_AGGREGATE: tuple t sums keys [key_off[t], key_off[t+1]) and checks
 // e(sum, H(msg_t)) e(-g1, sig_t) == 1.  MODE_AGGREGATE: one tuple, pairs (key_i, H(msg_i)) + (-g1, sig).
@@ -159,7 +161,9 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
                                const uint32_t* msg_off, uint32_t n_msgs, const uint8_t* sigs, uint32_t n_tuples,
                                bool force_fail_shape, int32_t* out_codes, RlcReq* rlc) {
     if (rlc && (mode != MODE_FAST_AGGREGATE || !s.use_vm)) return B200_ERR_BAD_ARG;
-    const bool registry = (keys == nullptr && index != nullptr);
+    // registry gather; with `keys` as well: `n_keys` EXTRA keys (deposits, bls-to-execution changes) validated by this call into
+    // the registry arrays' spare tail, named by indices reg_n + j
+    const bool registry = index != nullptr;
     const uint32_t T = n_tuples;
     const uint32_t n_g1 = (mode == MODE_FAST_AGGREGATE ? T : n_keys) + 1;  // + (-g1)
     const uint32_t n_pairs = (mode == MODE_FAST_AGGREGATE) ? 2 * T : (force_fail_shape ? 0 : n_msgs + 1);
@@ -241,11 +245,14 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     G2Aff* d_g2 = static_cast<G2Aff*>(s.g2pts.p);
     const G1Aff* key_aff = registry ? static_cast<const G1Aff*>(s.reg_aff.p) : static_cast<const G1Aff*>(s.key_aff.p);
     const int32_t* key_code = registry ? static_cast<const int32_t*>(s.reg_code.p) : static_cast<const int32_t*>(s.key_code.p);
+    // where the per-key kernel writes: the call's own arrays, or (registry + extra keys) the tail behind the reg_n resident keys
+    G1Aff* k1_aff = registry ? static_cast<G1Aff*>(s.reg_aff.p) + s.reg_n : static_cast<G1Aff*>(s.key_aff.p);
+    int32_t* k1_code = registry ? static_cast<int32_t*>(s.reg_code.p) + s.reg_n : static_cast<int32_t*>(s.key_code.p);
 
     // ---- small arrays + keys (stream A); signatures / messages on streams B, C (they overlap the 100 MB key copy)
     B200_CUDA_TRY(cudaMemcpyAsync(d_small, s.stage.p, small_bytes, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
-    if (!registry && n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
+    if (n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
     auto launch_small = [&]() -> int32_t {
         B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
@@ -259,9 +266,9 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
         B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
         return B200_SUCCESS;
     };
-    const bool have_k1 = !registry && n_keys;
+    const bool have_k1 = n_keys != 0;
     // packed CTAs only when there is a big per-key kernel to run under; alone (registry mode, small batches) they spread
-    set_small_cta(s.small_cta_override ? s.small_cta_override : ((have_k1 && s.small_order == 0 && T > 1024) ? 128 : 32));
+    set_small_cta(s.small_cta_override ? s.small_cta_override : ((have_k1 && n_keys >= 148u * 384u && s.small_order == 0 && T > 1024) ? 128 : 32));
     if (have_k1 && s.small_order == 1) {   // signatures / messages first, the per-key kernel only afterwards
         int32_t rc = launch_small();
         if (rc) return rc;
@@ -270,7 +277,7 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     }
     // ---- stream A: public keys
     B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
-    const uint32_t n_chunks = (mode == MODE_FAST_AGGREGATE && !rlc && s.use_vm && have_k1 && s.small_order == 0 && !force_fail_shape &&
+    const uint32_t n_chunks = (mode == MODE_FAST_AGGREGATE && !rlc && s.use_vm && have_k1 && !registry && s.small_order == 0 && !force_fail_shape &&
                                s.chunks > 1 && T >= s.chunk_min_tuples) ? std::min(s.chunks, BlsState::kMaxChunks) : 1u;
     const uint32_t* d_g1i = nullptr; const uint32_t* d_g2i = nullptr; const uint32_t* d_ptu = nullptr; const uint32_t* d_poff = nullptr;
     bool chunked = false;
@@ -327,8 +334,7 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     }
     if (!chunked) {
         if (have_k1) {
-            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, static_cast<G1Aff*>(s.key_aff.p),
-                               static_cast<int32_t*>(s.key_code.p), sa);
+            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, k1_aff, k1_code, sa);
             e.launches++;
         }
         if (!(have_k1 && s.small_order == 1)) {
@@ -747,8 +753,8 @@ int32_t b200_registry_load(const uint8_t* pks_flat, size_t n) {
     rc = bls_state(e, &s);
     if (rc) return rc;
     B200_CUDA_TRY(s->keys.reserve(n * 48 + 64));
-    B200_CUDA_TRY(s->reg_aff.reserve((n + 1) * sizeof(G1Aff)));
-    B200_CUDA_TRY(s->reg_code.reserve((n + 1) * 4));
+    B200_CUDA_TRY(s->reg_aff.reserve((n + kRegistryExtraKeys + 1) * sizeof(G1Aff)));   // + the tail `..._batch_mixed` validates into
+    B200_CUDA_TRY(s->reg_code.reserve((n + kRegistryExtraKeys + 1) * 4));
     if (n) B200_CUDA_TRY(cudaMemcpyAsync(s->keys.p, pks_flat, n * 48, cudaMemcpyHostToDevice, e.stream));
     B200_CUDA_TRY(cudaEventRecord(s->ev_k0, e.stream));
     launch_g1_validate(static_cast<const uint8_t*>(s->keys.p), uint32_t(n), static_cast<G1Aff*>(s->reg_aff.p),
@@ -776,28 +782,41 @@ int32_t b200_registry_key_codes(int32_t* out_codes, size_t n) {
     return B200_SUCCESS;
 }
 
-int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indices, const uint32_t* offsets, const uint8_t* msgs32,
-                                                 const uint8_t* sigs, size_t n_tuples, int32_t* out_codes) {
+static int32_t verify_batch_indexed(const uint8_t* extra_pks, size_t n_extra, const uint32_t* indices, const uint32_t* offsets,
+                                    const uint8_t* msgs32, const uint8_t* sigs, size_t n_tuples, int32_t* out_codes) {
     Engine& e = engine();
     Guard g(e);
     int32_t rc = check_ready(e);
     if (rc) return rc;
     if (n_tuples == 0) return B200_SUCCESS;
     if (!offsets || !msgs32 || !sigs || !out_codes || n_tuples > kMaxBatchTuples) return B200_ERR_BAD_ARG;
+    if ((n_extra && !extra_pks) || n_extra > kRegistryExtraKeys) return B200_ERR_BAD_ARG;
     BlsState* s;
     rc = bls_state(e, &s);
     if (rc) return rc;
+    if (n_extra && !s->reg_aff.p) { e.last_error = "no registry loaded"; return B200_ERR_BAD_ARG; }
     for (size_t t = 0; t < n_tuples; t++)
         if (offsets[t] > offsets[t + 1]) return B200_ERR_BAD_ARG;
     const uint32_t ni = offsets[n_tuples];
     if (ni && !indices) return B200_ERR_BAD_ARG;
     for (uint32_t i = 0; i < ni; i++)
-        if (indices[i] >= s->reg_n) { e.last_error = "validator index outside the loaded registry"; return B200_ERR_BAD_ARG; }
+        if (indices[i] >= s->reg_n + n_extra) { e.last_error = "validator index outside the loaded registry (+ extra keys)"; return B200_ERR_BAD_ARG; }
     std::vector<uint32_t> moff(n_tuples + 1);
     for (size_t t = 0; t <= n_tuples; t++) moff[t] = uint32_t(32 * t);
     static const uint32_t dummy = 0;
-    return run_verify(e, *s, MODE_FAST_AGGREGATE, nullptr, 0, indices ? indices : &dummy, ni, offsets, msgs32, moff.data(),
-                      uint32_t(n_tuples), sigs, uint32_t(n_tuples), false, out_codes);
+    return run_verify(e, *s, MODE_FAST_AGGREGATE, n_extra ? extra_pks : nullptr, uint32_t(n_extra), indices ? indices : &dummy, ni, offsets,
+                      msgs32, moff.data(), uint32_t(n_tuples), sigs, uint32_t(n_tuples), false, out_codes);
+}
+
+int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indices, const uint32_t* offsets, const uint8_t* msgs32,
+                                                 const uint8_t* sigs, size_t n_tuples, int32_t* out_codes) {
+    return verify_batch_indexed(nullptr, 0, indices, offsets, msgs32, sigs, n_tuples, out_codes);
+}
+
+int32_t b200_fast_aggregate_verify_batch_mixed(const uint8_t* extra_pks, size_t n_extra, const uint32_t* indices,
+                                               const uint32_t* offsets, const uint8_t* msgs32, const uint8_t* sigs,
+                                               size_t n_tuples, int32_t* out_codes) {
+    return verify_batch_indexed(extra_pks, n_extra, indices, offsets, msgs32, sigs, n_tuples, out_codes);
 }
 
 // crypto/bls.rs:114-132 — `public_keys: &[&PublicKey]` is an array of pointers into the validator registry

@@ -409,24 +409,14 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
         }
     }
     if (trace) cudaEventRecord(tev[1], s);
-    // Full re-hash of a RESIDENT state: the stage chains of everything except the Validator list (five latency-bound
-    // launches over ~0.7 M hashes) run on the idle copy stream UNDER the Validator kernel (8.4 M hashes, throughput-bound)
-    // instead of after it; the list's own upper levels follow once both are done.
-    bool side_stages = false;
-    if (!sparse && copy == COPY_NONE && !validators_launched && validator_jobs_.size() == 1) {
-        cudaStream_t cs = e.copy_stream;
-        B200_CUDA_TRY(cudaEventRecord(e.ev_copy[16], s));           // plan upload + earlier work on the compute stream
-        B200_CUDA_TRY(cudaStreamWaitEvent(cs, e.ev_copy[16], 0));
-        launch_stages([&](const PJob& pj) { return !from_validators(pj); }, cs);
-        B200_CUDA_TRY(cudaEventRecord(e.ev_copy[15], cs));
-        side_stages = true;
-    }
+    // (Measured and dropped, round 2 call 16: running the non-Validator stage chains on the copy stream UNDER the Validator
+    // kernel made the resident full re-hash slower, 1.60 -> 1.74 ms — the chains' CTAs take SM slots from the kernel that
+    // is the critical path, and the join adds two event waits.)
     if (!validators_launched)
         for (auto& pj : validator_jobs_) {
             if (sparse && pj.chain >= 0) continue;
             launch_validators(materialize(pj), s); e.launches++;
         }
-    if (side_stages) B200_CUDA_TRY(cudaStreamWaitEvent(s, e.ev_copy[15], 0));
     // incremental mode: the arena is the resident state's own, so the outputs of a dense job whose staged field did not
     // change since the previous root are still valid — only fields hit by `changed_host_ranges` are re-hashed
     std::vector<char> copy_changed(copies_.size(), sparse ? 0 : 1);
@@ -437,7 +427,7 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     launch_stages([&](const PJob& pj) {
         if (sparse && pj.chain >= 0) return false;
         if (sparse && pj.copy >= 0 && !copy_changed[size_t(pj.copy)]) return false;
-        if ((pipelined || side_stages) && !from_validators(pj)) return false;   // already launched, under the list's transfer / kernel
+        if (pipelined && !from_validators(pj)) return false;   // already launched, under the Validator list's transfer
         return true;
     }, s);
     if (trace) cudaEventRecord(tev[2], s);

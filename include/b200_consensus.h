@@ -219,6 +219,13 @@ B200_API int32_t b200_registry_key_codes(int32_t* out_codes, size_t n);
 B200_API int32_t b200_fast_aggregate_verify_batch_indexed(const uint32_t* indices, const uint32_t* offsets,
                                                           const uint8_t* msgs32, const uint8_t* sigs, size_t n_tuples,
                                                           int32_t* out_codes);
+/* Registry mode for a whole block's signature set in ONE call: `extra_pks` are the n_extra (<= 65 536) 48-byte keys that
+ * are not in the registry because they arrive in the block itself (deposits `phase0/block_processing.rs:387-392`, bls-to-
+ * execution changes `capella/block_processing.rs:43-56`); they are decompressed + validated by this call exactly like
+ * the strict path does, and an index i >= n_registry names extra key i - n_registry.  Codes as the strict path's. */
+B200_API int32_t b200_fast_aggregate_verify_batch_mixed(const uint8_t* extra_pks, size_t n_extra, const uint32_t* indices,
+                                                        const uint32_t* offsets, const uint8_t* msgs32, const uint8_t* sigs,
+                                                        size_t n_tuples, int32_t* out_codes);
 /* RLC whole-batch check over registry indices, and over all ranks of the communicator: every rank passes the same batch
  * and the same (non-NULL) seed, verifies its block, and ONE ncclAllGather moves the per-rank Gt partial (576 B) and G2
  * partial (288 B); every rank then finishes the same final exponentiation and returns the same boolean. */

@@ -124,6 +124,35 @@ def test_registry_mode_matches_strict(engine):
     assert got.tolist() == [c["code"] for c in cases]
 
 
+def test_mixed_mode_extra_keys_validated_in_call(engine):
+    """`..._batch_mixed`: every other distinct key lives in the registry, the rest arrive as extra keys (incl. the golden
+    cases' undecodable / infinite / off-curve / out-of-subgroup keys) — same codes as the strict path, twice in a row
+    (the registry's spare tail is reused), and an index past registry + extras is refused."""
+    cases = [c for c in FAV if len(c["msg"]) == 64]
+    uniq = sorted({p for c in cases for p in c["pks"]})
+    in_reg = uniq[::2]
+    extra = uniq[1::2]
+    reg = crypto.Registry(np.frombuffer(b"".join(bytes.fromhex(p) for p in in_reg), dtype=np.uint8))
+    pos = {p: i for i, p in enumerate(in_reg)}
+    pos.update({p: len(in_reg) + j for j, p in enumerate(extra)})
+    idx = np.array([pos[p] for c in cases for p in c["pks"]], dtype=np.uint32)
+    off = np.cumsum([0] + [len(c["pks"]) for c in cases]).astype(np.uint32)
+    msgs = np.frombuffer(b"".join(bytes.fromhex(c["msg"]) for c in cases), dtype=np.uint8)
+    sigs = np.frombuffer(b"".join(bytes.fromhex(c["sig"]) for c in cases), dtype=np.uint8)
+    xk = np.frombuffer(b"".join(bytes.fromhex(p) for p in extra), dtype=np.uint8)
+    want = [c["code"] for c in cases]
+    for _ in range(2):
+        assert reg.verify_batch(idx, off, msgs, sigs, extra_keys=xk).tolist() == want
+    bad = idx.copy()
+    bad[0] = len(uniq)
+    with pytest.raises(Exception):
+        reg.verify_batch(bad, off, msgs, sigs, extra_keys=xk)
+    with pytest.raises(Exception):      # extra-key indices without the extra keys
+        reg.verify_batch(idx, off, msgs, sigs)
+    # the registry itself is untouched by the calls
+    assert crypto.Registry.key_codes(reg).tolist() == [c for c in reg.key_codes()]
+
+
 @pytest.mark.parametrize("case", GOLDEN["aggregate_verify"], ids=lambda c: c["name"])
 def test_aggregate_verify(engine, case):
     pks = [bytes.fromhex(p) for p in case["pks"]]
