@@ -37,6 +37,7 @@ struct BlsState {
     uint32_t chunks = 1, chunk_min_tuples = 2048;
     int chunk_k1_cta = 128;
     bool chunk_alt = true;
+    bool key_split = true;   // B200_BLS_KEY_SPLIT / b200_tune("bls_key_split")
     cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp, gath;
     // RLC whole-batch check (bls_rlc.cu): Jacobian aggregates, scaled points, reduction ping-pong, zeros, indices, exchange
@@ -80,6 +81,7 @@ static int32_t bls_state(Engine& e, BlsState** out) {
         if (const char* v = getenv("B200_BLS_CHUNK_MIN_TUPLES")) s->chunk_min_tuples = uint32_t(std::max(2, atoi(v)));
         if (const char* v = getenv("B200_BLS_CHUNK_K1_CTA")) s->chunk_k1_cta = atoi(v);
         if (const char* v = getenv("B200_BLS_CHUNK_ALT")) s->chunk_alt = atoi(v) != 0;
+        if (const char* v = getenv("B200_BLS_KEY_SPLIT")) s->key_split = atoi(v) != 0;
         int prio_d = prio;
         if (const char* v = getenv("B200_PAIR_STREAM_PRIORITY")) prio_d = atoi(v);
         B200_CUDA_TRY(cudaStreamCreateWithPriority(&s->sd, cudaStreamNonBlocking, prio_d));
@@ -252,7 +254,16 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     // ---- small arrays + keys (stream A); signatures / messages on streams B, C (they overlap the 100 MB key copy)
     B200_CUDA_TRY(cudaMemcpyAsync(d_small, s.stage.p, small_bytes, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_in, sa));
-    if (n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(n_keys) * 48, cudaMemcpyHostToDevice, sa));
+    const bool have_k1 = n_keys != 0;
+    const uint32_t n_chunks = (mode == MODE_FAST_AGGREGATE && !rlc && s.use_vm && have_k1 && !registry && s.small_order == 0 && !force_fail_shape &&
+                               s.chunks > 1 && T >= s.chunk_min_tuples) ? std::min(s.chunks, BlsState::kMaxChunks) : 1u;
+    // Big strict batches: the first kSplitWaves full waves of the per-key kernel start as soon as THEIR keys have arrived; the rest of
+    // the key bytes (~90 MB at T = 4096) cross PCIe on stream E under that first launch, and the second launch follows them there
+    // (two streams, so its CTAs fill the first launch's draining tail).  b200_tune("bls_key_split", 0) restores the single copy.
+    constexpr uint32_t kSplitWaves = 4, kSplitKeys = kSplitWaves * 148u * 384u;
+    const uint32_t k_split = (s.key_split && have_k1 && !registry && n_chunks == 1 && s.small_order == 0 && n_keys >= 4u * kSplitKeys)
+                                 ? kSplitKeys : n_keys;
+    if (n_keys) B200_CUDA_TRY(cudaMemcpyAsync(s.keys.p, keys, size_t(k_split) * 48, cudaMemcpyHostToDevice, sa));
     B200_CUDA_TRY(cudaEventRecord(s.ev_k0, sa));
     auto launch_small = [&]() -> int32_t {
         B200_CUDA_TRY(cudaStreamWaitEvent(sb, s.ev_in, 0));
@@ -266,7 +277,6 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
         B200_CUDA_TRY(cudaEventRecord(s.ev_c, sc));
         return B200_SUCCESS;
     };
-    const bool have_k1 = n_keys != 0;
     // packed CTAs only when there is a big per-key kernel to run under; alone (registry mode, small batches) they spread
     set_small_cta(s.small_cta_override ? s.small_cta_override : ((have_k1 && n_keys >= 148u * 384u && s.small_order == 0 && T > 1024) ? 128 : 32));
     if (have_k1 && s.small_order == 1) {   // signatures / messages first, the per-key kernel only afterwards
@@ -277,8 +287,6 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     }
     // ---- stream A: public keys
     B200_CUDA_TRY(cudaEventRecord(s.ev_d0, sa));
-    const uint32_t n_chunks = (mode == MODE_FAST_AGGREGATE && !rlc && s.use_vm && have_k1 && !registry && s.small_order == 0 && !force_fail_shape &&
-                               s.chunks > 1 && T >= s.chunk_min_tuples) ? std::min(s.chunks, BlsState::kMaxChunks) : 1u;
     const uint32_t* d_g1i = nullptr; const uint32_t* d_g2i = nullptr; const uint32_t* d_ptu = nullptr; const uint32_t* d_poff = nullptr;
     bool chunked = false;
     const G1Aff* pair_g1 = d_g1;
@@ -334,7 +342,7 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     }
     if (!chunked) {
         if (have_k1) {
-            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), n_keys, k1_aff, k1_code, sa);
+            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), k_split, k1_aff, k1_code, sa, k_split < n_keys ? 384 : 0);
             e.launches++;
         }
         if (!(have_k1 && s.small_order == 1)) {
@@ -343,6 +351,16 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
             }
             int32_t rc = launch_small();
             if (rc) return rc;
+        }
+        if (k_split < n_keys) {   // the remaining keys: copy strictly after the first part's (one PCIe link), then their launch
+            B200_CUDA_TRY(cudaStreamWaitEvent(s.se, s.ev_k0, 0));
+            B200_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(s.keys.p) + size_t(k_split) * 48, keys + size_t(k_split) * 48,
+                                          size_t(n_keys - k_split) * 48, cudaMemcpyHostToDevice, s.se));
+            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p) + size_t(k_split) * 48, n_keys - k_split, k1_aff + k_split,
+                               k1_code + k_split, s.se, 384);
+            e.launches++;
+            B200_CUDA_TRY(cudaEventRecord(s.ev_ck[0], s.se));
+            B200_CUDA_TRY(cudaStreamWaitEvent(sa, s.ev_ck[0], 0));
         }
         B200_CUDA_TRY(cudaEventRecord(s.ev_d1, sa));
         if (s.trace) cudaEventRecord(s.ev_t[0], sa);
@@ -532,6 +550,7 @@ int32_t b200_tune(const char* knob, int64_t value) {
     else if (k == "bls_chunk_min_tuples") s->chunk_min_tuples = uint32_t(std::max<int64_t>(2, value));
     else if (k == "bls_chunk_k1_cta") s->chunk_k1_cta = int(value);
     else if (k == "bls_chunk_alt") s->chunk_alt = value != 0;
+    else if (k == "bls_key_split") s->key_split = value != 0;
     else if (k == "vm_team16_max") set_vm_team16_max(uint32_t(std::max<int64_t>(0, value)));
     else if (k == "vm_cta") set_vm_cta(int(value));
     else return B200_ERR_BAD_ARG;
