@@ -202,6 +202,11 @@ __global__ void k_fp_selftest(uint32_t n, uint32_t seed, uint32_t* out_mismatch)
     if ((i & 63) == 0 && !fp_is_zero(a)) {
         fp_inv(t, a); fp_mul(t, t, a);
         if (!fp_eq(t, fp_one())) bad++;
+        Fp k, f;                       // the shift-and-add inverse (the device's fp_inv) against the exponentiation
+        fp_inv_kaliski(k, a); fp_inv_fermat(f, a);
+        if (!fp_eq(k, f)) bad++;
+        fp_inv_kaliski(k, fp_zero());
+        if (!fp_is_zero(k)) bad++;
     }
     if (bad) atomicAdd(out_mismatch, bad);
 }

@@ -3,7 +3,9 @@
 // the signing roots.  One thread per signature / message; these kernels see only T (thousands) of items, so
 // they run concurrently with the wide G1 kernels on a second stream.
 #define B200_FP_MUL_CALL 1
+#if !defined(B200_G2_INLINE_FP2)     // A/B: Fp2 products inlined into the curve routines (fewer calls, operands stay in registers)
 #define B200_FP2_NOINLINE 1
+#endif
 #define B200_TOWER_NOINLINE 1
 #include <cuda_runtime.h>
 
@@ -20,7 +22,10 @@ namespace {
 // table in shared memory 16.7 ms; uncapped (234-255 registers) + shared table 24.4 ms — the by-value call ABI of this
 // TU saves/restores more registers around every product when the caller holds more of them.
 constexpr int kSmallCta = 32;
-#define B200_G2_BOUNDS __maxnreg__(128)
+#if !defined(B200_G2_MAXREG)
+#define B200_G2_MAXREG 128
+#endif
+#define B200_G2_BOUNDS __maxnreg__(B200_G2_MAXREG)
 __global__ void B200_G2_BOUNDS k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,
                                                        int32_t* __restrict__ sig_code) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -192,6 +192,54 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_merkle_stage(const __gr
 }
 
 
+// ---- folded upper levels: one pair-hash per thread per level, levels separated by __syncthreads (CoopJob, ssz_kernels.cuh)
+__global__ void __launch_bounds__(kStageThreads) k_merkle_coop(const __grid_constant__ CoopDesc cd) {
+    __shared__ uint32_t buf[2][kStageThreads][8];
+    int j = 0;
+#pragma unroll 1
+    for (int k = 1; k < cd.njobs; k++)
+        if (blockIdx.x >= cd.jobs[k].block_begin) j = k;
+    const CoopJob& cj = cd.jobs[j];
+    const uint32_t L = cj.nlev[0] + cj.nlev[1] + cj.nlev[2];     // 1..9
+    const uint64_t cta = blockIdx.x - cj.block_begin;
+    const uint32_t t = threadIdx.x;
+    Job first{};   // the first job's input side, for fetch()
+    first.src = cj.src; first.n_in = cj.n_in; first.level = cj.level; first.raw = cj.raw;
+    uint32_t done = 0;          // levels completed
+    int slot = 0;               // which of the folded jobs the next boundary belongs to
+    uint32_t boundary = cj.nlev[0];
+#pragma unroll 1
+    for (uint32_t lv = 1; lv <= L; lv++) {
+        const uint32_t width = 1u << (L - lv);              // nodes this CTA produces at this level
+        uint32_t out[8];
+        if (t < width) {
+            uint32_t l[8], r[8];
+            if (lv == 1) {
+                const uint64_t i0 = (cta << L) + 2ull * t;
+                fetch(first, cd.zero_nodes, i0, l);
+                fetch(first, cd.zero_nodes, i0 + 1, r);
+            } else {
+#pragma unroll
+                for (int w = 0; w < 8; w++) { l[w] = buf[lv & 1][2 * t][w]; r[w] = buf[lv & 1][2 * t + 1][w]; }
+            }
+            hash_pair_words(l, r, out);
+#pragma unroll
+            for (int w = 0; w < 8; w++) buf[(lv + 1) & 1][t][w] = out[w];
+        }
+        done = lv;
+        if (done == boundary) {                              // a folded job ends here: its outputs go to the arena
+            if (t < width) {
+                const uint64_t idx = cta * width + t;
+                const uint64_t n_out = (cj.n_in + (1ull << done) - 1) >> done;
+                if (idx < n_out) store_node(cj.dst[slot] + idx * 8, out);
+            }
+            slot++;
+            if (slot < 3) boundary += cj.nlev[slot];
+        }
+        __syncthreads();
+    }
+}
+
 // ---- dirty-path variants (incremental re-hash of a device-resident state) --------------------
 // Same per-thread work as the dense kernels, but thread t handles output sel[t] of the job instead of output t.
 __global__ void __launch_bounds__(kStageThreads) k_validator_roots_sparse(const __grid_constant__ Job jb,
@@ -307,6 +355,11 @@ void launch_stage(const StageDesc& sd, void* stream) {
     case 4: k_merkle_stage<4><<<sd.nblocks, kStageThreads, 0, st>>>(sd); break;
     default: k_merkle_stage<3><<<sd.nblocks, kStageThreads, 0, st>>>(sd); break;
     }
+}
+
+void launch_coop(const CoopDesc& cd, void* stream) {
+    if (cd.nblocks == 0) return;
+    k_merkle_coop<<<cd.nblocks, kStageThreads, 0, static_cast<cudaStream_t>(stream)>>>(cd);
 }
 
 void launch_sparse(const Job& jb, const uint32_t* zero_nodes, const uint32_t* sel, uint32_t n_sel, void* stream) {

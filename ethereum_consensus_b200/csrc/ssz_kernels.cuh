@@ -27,6 +27,29 @@ struct Job {
 constexpr int kMaxJobsPerStage = 24;
 constexpr int kStageThreads = 256;
 
+// Up to three CONSECUTIVE reduce jobs of one field (job k+1 reads what job k wrote) folded into one launch: a CTA owns
+// 2^L inputs (L = sum of the jobs' levels <= 9), hashes them level by level in shared memory — one pair-hash per thread
+// per level, __syncthreads between levels — and writes every job's output nodes where the separate launches would have.
+// 9 levels cost 9 pair-hash latencies instead of the 21 of three thread-per-subtree stages: the upper, latency-bound
+// part of a big list's tree (k_merkle_stage stays for the wide, throughput-bound lower stages).
+struct CoopJob {
+    const void* src;       // inputs of the first job
+    uint32_t* dst[3];      // outputs of each folded job (node arena)
+    uint64_t n_in;         // inputs of the first job
+    uint32_t level;        // tree level of those inputs
+    uint32_t nlev[3];      // levels folded by each job (0 = unused slot)
+    uint32_t raw;          // first job's inputs are raw SSZ bytes
+    uint32_t block_begin;
+};
+constexpr int kMaxCoopJobs = 12;
+struct CoopDesc {
+    CoopJob jobs[kMaxCoopJobs];
+    int njobs;
+    uint32_t nblocks;
+    const uint32_t* zero_nodes;
+};
+void launch_coop(const CoopDesc& cd, void* stream);
+
 struct StageDesc {
     Job jobs[kMaxJobsPerStage];
     int njobs;

@@ -294,11 +294,45 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
     static cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (trace && !tev[0]) for (auto& ev : tev) cudaEventCreate(&ev);
     bool validators_launched = false;
-    // stage launches over the jobs `pick` accepts (at most kMaxJobsPerStage jobs per launch)
+    // stage launches over the jobs `pick` accepts (at most kMaxJobsPerStage jobs per launch).  Once a list is down to
+    // kCoopMaxInputs nodes its remaining reduce jobs are latency-bound (7 dependent pair-hashes per thread and launch): up to
+    // three consecutive ones are folded into ONE cooperative launch (k_merkle_coop: a pair-hash per thread per level), which
+    // writes the same nodes to the same arena slots — the dirty-path re-hash still finds every level.  B200_SSZ_FOLD=0: off.
+    static const bool fold = !(getenv("B200_SSZ_FOLD") && atoi(getenv("B200_SSZ_FOLD")) == 0);
+    constexpr uint64_t kCoopMaxInputs = uint64_t(1) << 17;
     auto launch_stages = [&](auto&& pick, cudaStream_t on) {
-        for (auto& stage_all : stages_) {
+        std::vector<std::vector<char>> folded(stages_.size());
+        for (size_t si = 0; si < stages_.size(); si++) folded[si].assign(stages_[si].size(), 0);
+        for (size_t si = 0; si < stages_.size(); si++) {
+            auto& stage_all = stages_[si];
             std::vector<PJob> stage;
-            for (auto& pj : stage_all) if (pick(pj)) stage.push_back(pj);
+            std::vector<CoopJob> coop;
+            std::vector<uint32_t> coop_levels;
+            for (size_t k = 0; k < stage_all.size(); k++) {
+                const PJob& pj = stage_all[k];
+                if (folded[si][k] || !pick(pj)) continue;
+                if (!(fold && pj.type == JOB_REDUCE && pj.nlev > 0 && pj.n_in <= kCoopMaxInputs)) { stage.push_back(pj); continue; }
+                const Job j0 = materialize(pj);
+                CoopJob cj{};
+                cj.src = j0.src; cj.dst[0] = j0.dst; cj.n_in = pj.n_in; cj.level = pj.level; cj.nlev[0] = pj.nlev; cj.raw = pj.raw;
+                uint32_t L = pj.nlev;
+                uint32_t prev_dst = pj.dst;
+                int slot = 1;
+                for (size_t s2 = si + 1; s2 < stages_.size() && slot < 3; s2++) {
+                    int found = -1;
+                    for (size_t k2 = 0; k2 < stages_[s2].size(); k2++) {
+                        const PJob& nx = stages_[s2][k2];
+                        if (!folded[s2][k2] && nx.type == JOB_REDUCE && nx.nlev > 0 && !nx.raw && nx.src.in_arena && nx.src.off == prev_dst &&
+                            L + nx.nlev <= 9 && pick(nx)) { found = int(k2); break; }
+                    }
+                    if (found < 0) break;
+                    const PJob& nx = stages_[s2][size_t(found)];
+                    cj.dst[slot] = d_arena + nx.dst * 8; cj.nlev[slot] = nx.nlev;
+                    L += nx.nlev; prev_dst = nx.dst; folded[s2][size_t(found)] = 1; slot++;
+                }
+                coop.push_back(cj);
+                coop_levels.push_back(L);
+            }
             for (size_t b0 = 0; b0 < stage.size(); b0 += kMaxJobsPerStage) {
                 StageDesc sd{};
                 sd.zero_nodes = d_arena;
@@ -313,6 +347,21 @@ int32_t SszPlan::run(Engine& e, DevBuf& arena, DevBuf& fields, DevBuf& planbuf, 
                 }
                 sd.nblocks = nb;
                 launch_stage(sd, on);
+                e.launches++;
+            }
+            for (size_t b0 = 0; b0 < coop.size(); b0 += kMaxCoopJobs) {
+                CoopDesc cd{};
+                cd.zero_nodes = d_arena;
+                uint32_t nb = 0;
+                const size_t eidx = std::min(coop.size(), b0 + kMaxCoopJobs);
+                for (size_t k = b0; k < eidx; k++) {
+                    CoopJob cj = coop[k];
+                    cj.block_begin = nb;
+                    nb += uint32_t((cj.n_in + (uint64_t(1) << coop_levels[k]) - 1) >> coop_levels[k]);
+                    cd.jobs[cd.njobs++] = cj;
+                }
+                cd.nblocks = nb;
+                launch_coop(cd, on);
                 e.launches++;
             }
         }

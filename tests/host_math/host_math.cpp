@@ -192,6 +192,15 @@ extern "C" HM void hm_fpl_op(int op, const uint32_t* a, const uint32_t* b, uint3
     for (int i = 0; i < 12; i++) out[i] = r.v.l[i];
 }
 
+// ---- Kaliski inverse (fp.cuh, the device's fp_inv) against the Fermat exponentiation: out = [kaliski | fermat], 12 limbs each
+extern "C" HM void hm_fp_inv_both(const uint32_t* a, uint32_t* out) {
+    Fp x, k, f;
+    for (int i = 0; i < 12; i++) x.l[i] = a[i];
+    fp_inv_kaliski(k, x);
+    fp_inv_fermat(f, x);
+    for (int i = 0; i < 12; i++) { out[i] = k.l[i]; out[12 + i] = f.l[i]; }
+}
+
 // ---- Fp2 VM (lane-parallel pairing programs) on the host: scheduled program == direct evaluation, bit for bit
 #include "../../ethereum_consensus_b200/csrc/pairing_vm.cuh"
 static void vm_consts(Fp2* c) { for (int i = 0; i < kVmConsts; i++) vm_const_to_mont(c[i], h_vm_consts[i]); }

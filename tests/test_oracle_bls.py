@@ -250,6 +250,27 @@ def test_lazily_reduced_field_on_operands_up_to_2p(host_math):
     assert worst < 1.41 * P + 1     # the bound DESIGN.md section 4 derives: a b / R + p < (4p / R) p + p
 
 
+def test_kaliski_inverse_equals_fermat_inverse(host_math):
+    """fp.cuh's device inverse (Kaliski almost-inverse + two products) on the host: the same Montgomery-form value as a^(p-2)
+    for 0, 1, p - 1, powers of two, R mod p, values whose loop runs the minimum / maximum number of rounds, and 3 000 random
+    elements — and that value really is the inverse."""
+    host_math.hm_fp_inv_both.argtypes = [C.c_void_p, C.c_void_p]
+    rnd = random.Random(2024)
+    A12, A24 = C.c_uint32 * 12, C.c_uint32 * 24
+    lim = lambda x: A12(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(12)])  # noqa: E731
+    P, R = bo.P, 1 << 384
+    edge = [0, 1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, R % P, R * R % P, pow(R, -1, P), (1 << 380), (1 << 380) + 1,
+            (1 << 255) - 19, 0xffffffff, 1 << 32, (1 << 352) - 1] + [1 << j for j in range(0, 381, 7)]
+    out = A24()
+    for x in edge + [rnd.randrange(P) for _ in range(3000)]:
+        host_math.hm_fp_inv_both(lim(x), out)
+        k = sum(int(out[i]) << (32 * i) for i in range(12))
+        f = sum(int(out[12 + i]) << (32 * i) for i in range(12))
+        assert k == f, hex(x)
+        if x:   # x = a R, k = a^-1 R  =>  x * k = R^2
+            assert x * k % P == R * R % P, hex(x)
+
+
 def test_pairing_vm_programs_match_direct_evaluation(host_math):
     """The statically scheduled lane-parallel Miller / final-exponentiation programs (tools/gen_pairing_vm.py), run by
     the product's interpreter on the host, reproduce miller_loop bit for bit and final_exp_is_one's verdict."""

@@ -191,6 +191,7 @@ def emit_c(name, ops, regs, res, two_inputs):
         elif op == "add.cc": c.append(f"    w = uint64_t({x}) + {y}; {d} = uint32_t(w); cc = uint32_t(w >> 32);\n")
         elif op == "addc.cc": c.append(f"    w = uint64_t({x}) + {y} + cc; {d} = uint32_t(w); cc = uint32_t(w >> 32);\n")
         elif op == "addc": c.append(f"    {d} = {x} + {y} + cc;\n")
+        elif op == "add": c.append(f"    {d} = {x} + {y};\n")
         elif op == "mov": c.append(f"    {d} = {x};\n")
         elif op == "shf.l.wrap": c.append(f"    {d} = ({y} << 1) | ({x} >> 31);\n")
         else: raise ValueError(op)
@@ -226,9 +227,28 @@ def emit_ptx(name, ops, regs, res, two_inputs):
     return c
 
 
+def split_carry_captures(ops, regs):
+    """EXPERIMENT (--split-carry), not used: `x += carry` written as `addc x, x, 0` comes out of ptxas as IMAD.X — on the FMA
+    pipe these kernels are bound by (31 per square, 22 per product: ~5 % of the pipe).  Writing it as a capture into a scratch
+    register plus a plain add was meant to move both to the ALU pipe; ptxas 12.9 instead materialises the capture as predicated
+    IMAD.MOVs (product: 7 -> 59 IMAD.MOV, square: 15 -> 112), still on the FMA pipe and more of them.  Checked in SASS only."""
+    out = []
+    for op, d, x, y, z in ops:
+        if op == "addc" and y == "0" and x != "0":
+            out.append(("addc", "ct", "0", "0", None))
+            out.append(("add", d, x, "ct", None))
+        else:
+            out.append((op, d, x, y, z))
+    return out, (regs + ["ct"] if "ct" not in regs else regs)
+
+
 def main():
+    import sys
     mul_ops, mul_regs, mul_res = build_mul()
     sqr_ops, sqr_regs, sqr_res = build_sqr()
+    if "--split-carry" in sys.argv:
+        mul_ops, mul_regs = split_carry_captures(mul_ops, mul_regs)
+        sqr_ops, sqr_regs = split_carry_captures(sqr_ops, sqr_regs)
     out = ["// GENERATED by tools/gen_fp_mul_ptx.py — do not edit.  Included from fp.cuh (needs B200_HD, B200_FP_N0).\n#pragma once\n\nnamespace b200 {\n\n"]
     out.append("// C emulations of the PTX instruction lists below (same order, explicit carry flag `cc`).  Results in [0, 2p).\n")
     out += emit_c("fp_mul_emul_core", mul_ops, mul_regs, mul_res, True)
