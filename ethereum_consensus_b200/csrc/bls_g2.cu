@@ -3,7 +3,13 @@
 // the signing roots.  One thread per signature / message; these kernels see only T (thousands) of items, so
 // they run concurrently with the wide G1 kernels on a second stream.
 #define B200_FP_MUL_CALL 1
-#if !defined(B200_G2_INLINE_FP2)     // A/B: Fp2 products inlined into the curve routines (fewer calls, operands stay in registers)
+// Fp2 products are INLINED into the curve routines here and the kernels may use 255 registers: these kernels run one or two
+// warps per SM, so the only thing that matters is the length of one thread's dependent chain — and at T = 4096 the 3-5 KB
+// stack frames of the earlier build (Fp2 products as calls, 128 registers) overflowed L1.  Measured (profiles/r2_ab_variants.txt,
+// calls 22 / 23): the step's wait for these kernels in registry mode 7.95 -> 4.97 ms at T = 4096 (either change alone: 7.7 / 6.4),
+// registry step 10.15 -> 9.90 ms at T = 1024; strict step unchanged (116.7 ms: they hide under the per-key kernel).
+// -DB200_G2_FP2_CALLS / -DB200_G2_MAXREG=128 restore the earlier build.
+#if defined(B200_G2_FP2_CALLS)
 #define B200_FP2_NOINLINE 1
 #endif
 #define B200_TOWER_NOINLINE 1
@@ -16,14 +22,13 @@ namespace b200 {
 namespace {
 
 // One warp per CTA: with only T items there is at most a warp or two per SM, so these kernels are latency-bound and
-// spread as 32-thread CTAs over every SM.  They run BEFORE the per-key kernel, not under it: measured on B200
-// (profiles/r1_tuning.md), any co-scheduling costs the per-key kernel more than these kernels take alone.
-// A/B on B200 (T=4096, both kernels together): 128-register cap + thread-local fp_pow table 14.4 ms; same cap with the
-// table in shared memory 16.7 ms; uncapped (234-255 registers) + shared table 24.4 ms — the by-value call ABI of this
-// TU saves/restores more registers around every product when the caller holds more of them.
+// spread as 32-thread CTAs over every SM (128-thread CTAs when they run under a big per-key kernel, capi_bls.cu).
+// Round 1 (Fp2 products as calls): 128-register cap 14.4 ms, uncapped 24.4 ms for both kernels at T = 4096 — with calls, more
+// registers in the caller meant more saves / restores around every product.  Round 2 inlines the Fp2 products and lifts the cap
+// (see the top of this file).
 constexpr int kSmallCta = 32;
 #if !defined(B200_G2_MAXREG)
-#define B200_G2_MAXREG 128
+#define B200_G2_MAXREG 255
 #endif
 #define B200_G2_BOUNDS __maxnreg__(B200_G2_MAXREG)
 __global__ void B200_G2_BOUNDS k_g2_sig_decode(const uint8_t* __restrict__ sigs, uint32_t n, G2Aff* __restrict__ out,

@@ -20,8 +20,8 @@ if os.environ.get("_VM_PROBE_CHILD") != "1":
             n = int(m.group(1))
             last = trace[k + n - 1] if k + n - 1 < len(trace) else ""
             k += n
-            sp = re.search(r"miller ([\d.]+) \| final ([\d.]+)", last)
-            print(m.group(2), f"| miller {sp.group(1)} final {sp.group(2)}" if sp else "", flush=True)
+            sp = re.search(r"K2 ([\d.]+) \| wait\(streamB\) ([\d.]+) \| miller ([\d.]+) \| final ([\d.]+)", last)
+            print(m.group(2), f"| K2 {sp.group(1)} G2-wait {sp.group(2)} miller {sp.group(3)} final {sp.group(4)}" if sp else "", flush=True)
         else:
             print(ln, flush=True)
     if p.returncode:
