@@ -12,7 +12,7 @@
 #if defined(B200_G2_FP2_CALLS)
 #define B200_FP2_NOINLINE 1
 #endif
-#define B200_TOWER_NOINLINE 1
+#define B200_TOWER_NOINLINE 1   // (a build with the curve routines inlined as well returned wrong verdicts on the GPU — not investigated, not offered)
 #include <cuda_runtime.h>
 
 #include "bls_kernels.cuh"

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) k_vm_miller(const uint32_t* __restrict__ 
     extern __shared__ uint32_t smem[];
     const uint32_t team_in_block = threadIdx.x / TEAM, lane = threadIdx.x % TEAM;
     const uint32_t i = blockIdx.x * (blockDim.x / TEAM) + team_in_block;
-    VmRfStrided rf{smem + team_in_block * (uint32_t(n_slots) * kVmSlotWords)};
+    VmRfStrided rf{smem + team_in_block * vm_team_words(uint32_t(n_slots))};
     bool active = i < n_pairs && !tuple_dead(pair_tuple[i], pk_code, flags, sig_code);
     bool trivial = false;  // a point at infinity: the pair contributes 1
     if (active) {
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) k_vm_final(const uint32_t* __restrict__ c
     extern __shared__ uint32_t smem[];
     const uint32_t team_in_block = threadIdx.x / TEAM, lane = threadIdx.x % TEAM;
     const uint32_t t = blockIdx.x * (blockDim.x / TEAM) + team_in_block;
-    VmRfStrided rf{smem + team_in_block * (uint32_t(n_slots) * kVmSlotWords)};
+    VmRfStrided rf{smem + team_in_block * vm_team_words(uint32_t(n_slots))};
     int32_t code_out = BLS_SUCCESS;
     bool active = false;
     if (t < n_tuples) {
@@ -184,7 +184,7 @@ int vm_load_programs(const uint32_t* blob, size_t n_words, void* stream) {
     if (!mr || !fr || mr > (1u << 20) || fr > (1u << 20) || ms < 12 || fs < 12 || ms > 255 || fs > 255) return 1;
     if (n_words != 18 + size_t(mr) * team + size_t(fr) * team) return 1;
     // one team's register file must fit a CTA's shared memory at the smallest CTA (one warp)
-    if (size_t(32 / team) * std::max(ms, fs) * kVmSlotWords * 4 > size_t(kVmMaxSmemBytes)) return 1;
+    if (size_t(32 / team) * vm_team_words(std::max(ms, fs)) * 4 > size_t(kVmMaxSmemBytes)) return 1;
     auto check = [&](const uint32_t* code, uint32_t rounds, uint32_t slots, const uint32_t* outs) {
         for (int k = 0; k < 6; k++) if (outs[k] >= slots) return false;
         for (size_t i = 0; i < size_t(rounds) * team; i++) {
@@ -233,9 +233,9 @@ static void launch_vm_miller_t(int slot, const G1Pre* g1, const uint32_t* g1_idx
                                uint32_t n_pairs, Fp12* f, cudaStream_t st) {
     const VmProgramDev& p = g_miller_prog[slot];
     int threads = g_vm_cta;
-    while (threads > 32 && size_t(threads / TEAM) * p.slots * kVmSlotWords * 4 > size_t(kVmMaxSmemBytes)) threads >>= 1;
+    while (threads > 32 && size_t(threads / TEAM) * vm_team_words(uint32_t(p.slots)) * 4 > size_t(kVmMaxSmemBytes)) threads >>= 1;
     const int teams = threads / TEAM;
-    const size_t smem = size_t(teams) * p.slots * kVmSlotWords * 4;
+    const size_t smem = size_t(teams) * vm_team_words(uint32_t(p.slots)) * 4;
     k_vm_miller<TEAM><<<(n_pairs + teams - 1) / teams, threads, smem, st>>>(
         p.d_code, g_d_consts, g1, g1_idx, g2, g2_idx, pair_tuple, pk_code, flags, sig_code, n_pairs, f, p.rounds, p.slots, p.outs);
 }
@@ -244,9 +244,9 @@ static void launch_vm_final_t(int slot, const Fp12* f, const uint32_t* pair_off,
                               const int32_t* sig_code, uint32_t n_tuples, int32_t* out_codes, cudaStream_t st) {
     const VmProgramDev& p = g_final_prog[slot];
     int threads = g_vm_cta;
-    while (threads > 32 && size_t(threads / TEAM) * p.slots * kVmSlotWords * 4 > size_t(kVmMaxSmemBytes)) threads >>= 1;
+    while (threads > 32 && size_t(threads / TEAM) * vm_team_words(uint32_t(p.slots)) * 4 > size_t(kVmMaxSmemBytes)) threads >>= 1;
     const int teams = threads / TEAM;
-    const size_t smem = size_t(teams) * p.slots * kVmSlotWords * 4;
+    const size_t smem = size_t(teams) * vm_team_words(uint32_t(p.slots)) * 4;
     k_vm_final<TEAM><<<(n_tuples + teams - 1) / teams, threads, smem, st>>>(
         p.d_code, g_d_consts, f, pair_off, pk_code, flags, sig_code, n_tuples, out_codes, p.rounds, p.slots, p.outs);
 }
