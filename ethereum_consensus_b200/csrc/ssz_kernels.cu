@@ -246,13 +246,18 @@ __global__ void __launch_bounds__(kStageThreads) k_validator_roots_sparse(const 
                                                                           const uint32_t* __restrict__ sel, uint32_t n_sel) {
     __shared__ __align__(16) uint32_t smem[(kStageThreads * 121 + 16) / 4 + 4];
     const uint32_t t = blockIdx.x * kStageThreads + threadIdx.x;
-    if (t >= n_sel) return;
-    const uint32_t rec = sel[t];
-    const uint8_t* g = reinterpret_cast<const uint8_t*>(jb.src) + uint64_t(rec) * 121u;
-    uint8_t* sb = reinterpret_cast<uint8_t*>(smem) + threadIdx.x * 121u;
-    for (int i = 0; i < 121; i++) sb[i] = g[i];  // each thread stages (and later reads) only its own record
-    // (smem_be_word loads whole words, so it touches neighbouring records' bytes, but only selects this record's)
-    __syncwarp();
+    const bool valid = t < n_sel;
+    const uint32_t rec = valid ? sel[t] : 0u;
+    if (valid) {
+        const uint8_t* g = reinterpret_cast<const uint8_t*>(jb.src) + uint64_t(rec) * 121u;
+        uint8_t* sb = reinterpret_cast<uint8_t*>(smem) + threadIdx.x * 121u;
+        for (int i = 0; i < 121; i++) sb[i] = g[i];  // each thread stages its own record
+    }
+    // smem_be_word loads whole words, which straddle the neighbouring threads' records (only this record's bytes are selected):
+    // a block-wide barrier, not a warp one, so that no neighbour is still storing into a word this thread reads
+    // (compute-sanitizer racecheck flagged the warp-level version; byte stores never clobbered the selected bytes, but it was a hazard)
+    __syncthreads();
+    if (!valid) return;
     uint32_t root[8];
     validator_root(smem, threadIdx.x * 121u, root);
     store_node(jb.dst + uint64_t(rec) * 8, root);
