@@ -70,7 +70,22 @@ class _Entry:
     signature: bytes
     tolerant: bool = False
     eth_variant: bool = False  # eth_fast_aggregate_verify semantics (sync aggregate)
-    indices: Optional[List[int]] = None  # validator indices of the signers when they come from state.validators
+    _indices: Optional[tuple] = None        # validator indices of the signers when they come from state.validators
+    _indices_np: Optional[np.ndarray] = None  # the same, packed once at collection time (verify() only concatenates)
+
+    @property
+    def indices(self) -> Optional[tuple]:
+        """Immutable on purpose: the packed copy verify() uses must not go stale behind an in-place edit."""
+        return self._indices
+
+    @indices.setter
+    def indices(self, value) -> None:
+        if value is None:
+            self._indices, self._indices_np = None, None
+        else:
+            self._indices_np = np.fromiter((int(i) for i in value), dtype=np.uint32)
+            self._indices_np.setflags(write=False)
+            self._indices = tuple(int(i) for i in self._indices_np)
 
 
 @dataclass
@@ -154,19 +169,19 @@ class SignatureSet:
         else:
             # ONE call for the whole set: signers named by validator index gather from the resident registry; keys carried
             # by the block (deposits, bls-to-execution changes) ride along as extra keys, validated in the same call
-            extra, idx = [], []
+            extra, parts = [], []
             for e in self.entries:
                 if e.indices is not None:
-                    idx.extend(e.indices)
+                    parts.append(e._indices_np)
                 else:
-                    for p in e.pubkeys:
-                        idx.append(registry.n + len(extra))
-                        extra.append(p)
-            off = np.cumsum([0] + [len(e.indices) if e.indices is not None else len(e.pubkeys) for e in self.entries]).astype(np.uint32)
+                    parts.append(np.arange(registry.n + len(extra), registry.n + len(extra) + len(e.pubkeys), dtype=np.uint32))
+                    extra.extend(e.pubkeys)
+            off = np.cumsum([0] + [len(q) for q in parts]).astype(np.uint32)
+            idx = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint32)
             msgs = np.frombuffer(b"".join(e.signing_root for e in self.entries), dtype=np.uint8)
             sigs = np.frombuffer(b"".join(e.signature for e in self.entries), dtype=np.uint8)
             xk = np.frombuffer(b"".join(extra), dtype=np.uint8) if extra else None
-            codes = registry.verify_batch(np.array(idx, dtype=np.uint32), off, msgs, sigs, extra_keys=xk).copy()
+            codes = registry.verify_batch(idx, off, msgs, sigs, extra_keys=xk).copy()
         for i, e in enumerate(self.entries):  # eth_fast_aggregate_verify: no participants + infinity signature is Ok
             if e.eth_variant and not e.pubkeys and e.signature == crypto.INFINITY_COMPRESSED_SIGNATURE:
                 codes[i] = 0

@@ -165,7 +165,7 @@ def collect_block_signature_set(registry, rows):
             # hand the pre-computed signing root in by entry surgery after checking the gather picked the same signers
             s.add_sync_aggregate([keys[i] for i in r["committee"]], r["bits"], r["sig"], 8_626_177, hashlib.sha256(b"prev").digest(), fork, gvr,
                                  committee_indices=r["committee"])
-            assert s.entries[-1].indices == r["indices"]
+            assert list(s.entries[-1].indices) == r["indices"]
             s.entries[-1].signing_root = r["root"]
         elif r["indices"] is not None:
             s.add_by_index(r["site"], keys, r["indices"], r["root"], r["sig"])
