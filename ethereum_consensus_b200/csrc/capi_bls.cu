@@ -38,6 +38,10 @@ struct BlsState {
     int chunk_k1_cta = 128;
     bool chunk_alt = true;
     bool key_split = true;   // B200_BLS_KEY_SPLIT / b200_tune("bls_key_split")
+    // CTA size of the first (4-wave) per-key launch of a split batch, the one the signature / message kernels run under: as three
+    // 128-thread CTAs per SM a side kernel's CTA displaces a third of an SM's per-key work instead of all of it
+    // (T = 4096: 116.84 -> 116.43 ms per step, profiles/r2_ab_variants.txt call 32)
+    int k1_first_cta = 128;
     cudaEvent_t ev_in = nullptr, ev_b = nullptr, ev_c = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     DevBuf keys, key_aff, key_code, g1pts, g1pre, pk_code, flags, sigs, g2pts, sig_code, msgs, small, f, out, h2c_tmp, gath;
     // RLC whole-batch check (bls_rlc.cu): Jacobian aggregates, scaled points, reduction ping-pong, zeros, indices, exchange
@@ -342,7 +346,7 @@ static int32_t run_verify_impl(Engine& e, BlsState& s, PairMode mode, const uint
     }
     if (!chunked) {
         if (have_k1) {
-            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), k_split, k1_aff, k1_code, sa, k_split < n_keys ? 384 : 0);
+            launch_g1_validate(static_cast<const uint8_t*>(s.keys.p), k_split, k1_aff, k1_code, sa, k_split < n_keys ? s.k1_first_cta : 0);
             e.launches++;
         }
         if (!(have_k1 && s.small_order == 1)) {
@@ -551,6 +555,8 @@ int32_t b200_tune(const char* knob, int64_t value) {
     else if (k == "bls_chunk_k1_cta") s->chunk_k1_cta = int(value);
     else if (k == "bls_chunk_alt") s->chunk_alt = value != 0;
     else if (k == "bls_key_split") s->key_split = value != 0;
+    else if (k == "bls_k1_first_cta") s->k1_first_cta = (value == 128) ? 128 : 384;
+    else if (k == "bls_small_cta") s->small_cta_override = int(value);
     else if (k == "vm_team16_max") set_vm_team16_max(uint32_t(std::max<int64_t>(0, value)));
     else if (k == "vm_cta") set_vm_cta(int(value));
     else return B200_ERR_BAD_ARG;

@@ -102,7 +102,7 @@ def test_chunked_pipeline_same_codes_on_ragged_golden_batch(engine):
         with pytest.raises(Exception):
             crypto.tune("no_such_knob", 1)
     finally:
-        for k, v in (("bls_chunks", 1), ("bls_chunk_min_tuples", 2048), ("bls_chunk_alt", 1), ("bls_chunk_k1_cta", 128), ("vm_cta", 32),
+        for k, v in (("bls_chunks", 1), ("bls_chunk_min_tuples", 2048), ("bls_chunk_alt", 1), ("bls_chunk_k1_cta", 128), ("vm_cta", 32), ("bls_k1_first_cta", 128), ("bls_small_cta", 0),
                      ("vm_team16_max", 2048)):
             crypto.tune(k, v)
 

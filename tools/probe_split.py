@@ -16,8 +16,9 @@ _lib.init(0)
 import torch
 pks, off, msgs, sigs = (bench.pin(w[k]) for k in ("pks", "off", "msgs", "sigs"))
 want = w["expect"].tolist()
-for split in (1, 0, 1, 0):
-    crypto.tune("bls_key_split", split)
+CONFIGS = [(1, 384, 0), (1, 128, 0), (1, 128, 64), (1, 128, 32), (1, 384, 64), (1, 384, 32), (1, 384, 0), (1, 128, 64)] if os.environ.get("B200_PROBE_CTA") else [(1, 384, 0), (0, 384, 0), (1, 384, 0), (0, 384, 0)]
+for split, first_cta, small_cta in CONFIGS:
+    crypto.tune("bls_key_split", split); crypto.tune("bls_k1_first_cta", first_cta); crypto.tune("bls_small_cta", small_cta)
     dev, wall = [], []
     for i in range(7):
         torch.cuda.synchronize()
@@ -27,5 +28,5 @@ for split in (1, 0, 1, 0):
         assert got.tolist() == want
         if i >= 2:
             dev.append(crypto.last_kernel_ms()); wall.append(dt)
-    print(f"T={T} K={K} G1_VARIANT={os.environ.get('B200_G1_VARIANT', 'default')} key_split={split}: device {min(dev):.2f} ms | end-to-end wall {min(wall):.2f} ms "
+    print(f"T={T} K={K} G1_VARIANT={os.environ.get('B200_G1_VARIANT', 'default')} key_split={split} k1_first_cta={first_cta} small_cta={small_cta or 'auto'}: device {min(dev):.2f} ms | end-to-end wall {min(wall):.2f} ms "
           f"(median {sorted(wall)[len(wall)//2]:.2f}) | per-key kernels {crypto.last_dominant_kernel_ms():.2f} ms", flush=True)
