@@ -8,6 +8,8 @@ import pytest
 
 from oracle import bls_oracle as bo
 
+ROOT = Path(__file__).resolve().parent.parent
+
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "bls_cases.json").read_text())
 F1, F2 = bo.F1, bo.F2
 
@@ -248,6 +250,29 @@ def test_lazily_reduced_field_on_operands_up_to_2p(host_math):
         host_math.hm_fpl_op(1, lim(a), lim(b), out); r = val(out); assert r < 2 * P and r % P == (a - b) % P
         host_math.hm_fpl_op(2, lim(a), lim(b), out); r = val(out); assert r < 2 * P and r % P == (-a) % P
     assert worst < 1.41 * P + 1     # the bound DESIGN.md section 4 derives: a b / R + p < (4p / R) p + p
+
+
+def test_adx_build_of_the_c_oracle_agrees_with_the_portable_build(oracle_bls_c):
+    """bench.py times oracle/liboracle_bls_adx.so (same source, -mbmi2 -madx) when the host CPU has both features: it must return
+    what the portable build returns — every golden fast_aggregate_verify case and a run of key validations."""
+    try:
+        flags = set(next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")).split())
+    except (OSError, StopIteration):
+        flags = set()
+    if not {"adx", "bmi2"} <= flags:
+        pytest.skip("host CPU without adx / bmi2")
+    adx = C.CDLL(str(ROOT / "oracle" / "liboracle_bls_adx.so"))
+    for lib in (adx, oracle_bls_c):
+        lib.orc_fast_aggregate_verify.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p]
+        lib.orc_key_validate.argtypes = [C.c_char_p]
+    golden = json.loads((ROOT / "tests" / "golden" / "bls_cases.json").read_text())
+    for c in golden["fast_aggregate_verify"]:
+        pks = b"".join(bytes.fromhex(p) for p in c["pks"])
+        m, sg = bytes.fromhex(c["msg"]), bytes.fromhex(c["sig"])
+        a = adx.orc_fast_aggregate_verify(pks, len(c["pks"]), m, len(m), sg)
+        assert a == oracle_bls_c.orc_fast_aggregate_verify(pks, len(c["pks"]), m, len(m), sg) == c["code"], c["name"]
+        for p in c["pks"][:4]:
+            assert adx.orc_key_validate(bytes.fromhex(p)) == oracle_bls_c.orc_key_validate(bytes.fromhex(p))
 
 
 def test_kaliski_inverse_equals_fermat_inverse(host_math):
